@@ -1,0 +1,40 @@
+"""Shared checks: run any object with the reference's surface against tests/golden/golden_v1.json.gz.
+
+Used twice: for the CPU oracle (not gpu) and for the CUDA `Tokenize` (gpu), so both are pinned to
+the same reference-generated vectors.
+"""
+import gzip
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_golden():
+    with gzip.open(os.path.join(HERE, "golden", "golden_v1.json.gz"), "rb") as f:
+        return json.loads(f.read().decode("ascii"))
+
+
+def _norm(out):
+    if "offset" in out:
+        out = dict(out)
+        out["offset"] = [list(p) for p in out["offset"]]
+    return out
+
+
+def check_case(tok, c, where=""):
+    kw = dict(c["kw"])
+    exp = c["out"]
+    if "raises" in exp:
+        try:
+            got = tok(c["text"], c["pair"], **kw)
+        except ValueError:
+            return
+        raise AssertionError("%s expected ValueError for %r / %r %r, got %r" % (where, c["text"], c["pair"], kw, got))
+    got = _norm(tok(c["text"], c["pair"], **kw))
+    assert got == _norm(exp), "%s mismatch for text=%r pair=%r kw=%r\n got=%r\n exp=%r" % (where, c["text"], c["pair"], kw, got, exp)
+
+
+def check_cases(tok, cases, where=""):
+    for i, c in enumerate(cases):
+        check_case(tok, c, "%s[%d]" % (where, i))
