@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py -- the encode hot path on N B200s (one process per GPU), next to the CPU restatement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): bundled vocab, 1,048,576 synthetic single sentences per GPU
+(3-13 words sampled from vocab.txt in proportion to their counts), max_len=128,
+padding + truncation.  One step = one pass of the whole batch through the CUDA pipeline.  With N GPUs
+every rank encodes its own shard of documents (no collective; shards concatenate), so scaling is weak.
+
+Prints ONE JSON line (rank 0).  `value` = real tokens/s with the text already resident in HBM and the
+[n,128] planes written to HBM; `e2e` = the same through Tokenize.encode_batch with host buffers (pinned
+host text in, pinned host planes out, copies inside the timed region); `roofline` = algorithmic bytes of
+the dominant kernel (k_rows_fixed) over its CUDA-event duration against the measured HBM copy bandwidth;
+`cpu_baseline` = oracle/ (the C restatement of tokenize.py) on this host's cores, a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DOCS = 1 << 20
+MAX_LEN = 128
+SEED = 1234
+L2_FLUSH_BYTES = 256 << 20
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        self.busy = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+        alt = {"hw_slowdown": "nvmlClocksThrottleReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksThrottleReasonHwThermalSlowdown",
+               "sw_thermal_slowdown": "nvmlClocksThrottleReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksThrottleReasonSwPowerCap"}
+        while not self.stop_flag:
+            try:
+                if self.busy:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k in names:
+                        bit = getattr(nv, names[k], None) or getattr(nv, alt[k], 0)
+                        if r & bit:
+                            self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nv and self.t.is_alive():
+            self.t.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def oracle_rate(tb, to, n_sample, threads, repeats=1):
+    """tokens/s of the CPU restatement on the first n_sample documents."""
+    from oracle.oracle import Oracle
+    o = Oracle()
+    sub = (tb[:to[n_sample]], to[:n_sample + 1])
+    best, toks = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = o.encode_batch(sub, None, max_len=MAX_LEN, threads=threads)
+        dt = time.perf_counter() - t0
+        toks = int(r["mask"].sum())
+        best = dt if best is None or dt < best else best
+    return toks / best, toks, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host CPU (oracle/ port, all host threads)."""
+    if rank != 0:
+        return
+    from genz_tokenize_b200 import workload
+    from oracle.oracle import Oracle
+    threads = Oracle.max_threads()
+    n_sample = 1 << 17
+    tb, to = workload.generate(SEED, n_sample, 3, 13, 0.0)
+    for _ in range(max(args.warmup, 0)):
+        oracle_rate(tb, to, 1 << 13, threads)
+    t_tot, tok_tot = 0.0, 0
+    for _ in range(args.steps):
+        rate, toks, dt = oracle_rate(tb, to, n_sample, threads)
+        t_tot += dt
+        tok_tot += toks
+    value = tok_tot / t_tot
+    in_bytes = int(to[n_sample])
+    line = {
+        "impl": "reference", "metric": "encode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": "bundled vocab, synthetic single sentences (3-13 words), max_len=128, padding+truncation (BASELINE configs[1])",
+                   "docs_per_step": n_sample, "note": "bounded sample of the 1,048,576-document batch; host CPU only"},
+        "input_gb_per_s": in_bytes * args.steps / t_tot / 1e9,
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": "%d of 1048576 documents per step, oracle/genztok_oracle.c with OpenMP over documents" % n_sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=N_DOCS, help="documents per GPU per step (default: the BASELINE config)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from genz_tokenize_b200 import Tokenize, workload
+    from genz_tokenize_b200 import _lib as L
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.docs
+    # shard by document: rank r owns chunk r of the global batch (generator chunks are 1M documents)
+    tb, to = workload.generate(SEED, n, 3, 13, 0.0, first_chunk=rank)
+    in_bytes = int(to[-1])
+    tok = Tokenize(devices=[local_rank])
+
+    # ---- device-resident leg ---------------------------------------------------------------------
+    pad = (-in_bytes) % 16 + 16
+    d_text = torch.from_numpy(np.concatenate([tb, np.zeros(pad, dtype=np.uint8)])).to(dev)
+    d_off = torch.from_numpy(to).to(dev)
+    out = {"input_ids": torch.empty((n, MAX_LEN), dtype=torch.int32, device=dev),
+           "attention_mask": torch.empty((n, MAX_LEN), dtype=torch.uint8, device=dev),
+           "row_len": torch.empty((n,), dtype=torch.int32, device=dev)}
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step():
+        tok.encode_device(d_text, d_off, max_len=MAX_LEN, out=out, text_bytes=in_bytes)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    tokens_per_step = int(out["attention_mask"].sum().item())
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = tok.launch_count()
+    sampler.busy = True
+    for a, b in ev:
+        flush.zero_()          # evict the batch and the tables from L2 (untimed)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    sampler.busy = False
+    if world > 1:
+        dist.barrier()
+    launches = tok.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- dominant-kernel duration (library-side CUDA events on the launching stream), outside the timed region
+    tok.set_profiling(True)
+    tok.profile_report(reset=True)
+    for _ in range(5):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    prof = tok.profile_report(reset=True)
+    tok.set_profiling(False)
+    k = prof.get("k_rows_fixed", {"launches": 1, "ms": float("nan")})
+    k_ms = k["ms"] / max(k["launches"], 1)
+    step_kernel_ms = sum(v["ms"] for v in prof.values()) / 5.0
+
+    # ---- end-to-end leg: public API, host buffers, copies inside the timed region ---------------------
+    lib = L.load()
+    hp = lib.genztok_host_alloc(in_bytes + 64)
+    import ctypes as C
+    pin_text = np.frombuffer((C.c_uint8 * in_bytes).from_address(hp), dtype=np.uint8)
+    pin_text[:] = tb
+    e2e_ms, h2d, d2h = 0.0, 0, 0
+    for i in range(args.e2e_steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        be = tok.encode_batch((pin_text, to), max_len=MAX_LEN)
+        checksum = int(be["row_len"][-1])      # the result is in host memory when the call returns
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_ms += dt * 1e3
+        h2d = in_bytes + to.nbytes
+        d2h = be["input_ids"].nbytes + be["attention_mask"].nbytes + be["row_len"].nbytes
+        e2e_tokens = int(be["real_tokens"])
+        del be
+    lib.genztok_host_free(hp)
+    clocks = sampler.stop()
+
+    # ---- max over ranks --------------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
+    s = torch.tensor([tokens_per_step, in_bytes, launches, e2e_tokens], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, k_ms = [float(x) for x in t.tolist()]
+    tot_tokens, tot_in_bytes, tot_launches, tot_e2e_tokens = [float(x) for x in s.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = dev_ms / args.steps
+    value = tot_tokens / (ms_per_step * 1e-3)
+    peak, peak_src = measured_hbm_peak()
+    alg_bytes = in_bytes + 8 * (n + 1) + n * MAX_LEN * (4 + 1)          # SURVEY.md §8(d4), per GPU per launch
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get("k_rows_fixed_dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "encode_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": "bundled vocab, %d synthetic single sentences per GPU (3-13 words), max_len=%d, padding+truncation (BASELINE configs[1])" % (n, MAX_LEN),
+                   "docs_per_gpu": n, "max_len": MAX_LEN, "sharding": "by document, no collective", "l2": "flushed between timed steps (256 MiB write)",
+                   "outputs": "input_ids int32 + attention_mask uint8 [n,128] + row_len"},
+        "input_gb_per_s": tot_in_bytes / (ms_per_step * 1e-3) / 1e9,
+        "alg_gb_per_s": world * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+        "hbm_frac_of_step": world * alg_bytes / (ms_per_step * 1e-3) / 1e9 / (world * peak),
+        "roofline": {"bound": "hbm", "kernel": "k_rows_fixed", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                     "kernels_ms_per_step": step_kernel_ms, "kernel_share_of_step": k_ms / step_kernel_ms if step_kernel_ms else None},
+        "e2e": {"value": tot_e2e_tokens / (e2e_ms / args.e2e_steps * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.e2e_steps, "api": "Tokenize.encode_batch(packed text in pinned host memory) -> pinned numpy planes"},
+        "gpu_launches": int(tot_launches),
+        "clocks": clocks,
+        "kernels": prof,
+    }
+    if not args.no_cpu:
+        threads = 0
+        try:
+            from oracle.oracle import Oracle
+            threads = Oracle.max_threads()
+            r1, _, _ = oracle_rate(tb, to, 1 << 15, 1)
+            rN, _, dtN = oracle_rate(tb, to, min(n, 1 << 18), threads)
+            line["cpu_baseline"] = {"value": rN, "unit": "tokens/s", "cores": threads, "kind": "port", "single_thread_value": r1,
+                                    "sample": "oracle/genztok_oracle.c (C restatement of tokenize.py, no memoisation) on the first %d documents with %d OpenMP threads "
+                                              "(%.1f s); single thread on the first %d" % (min(n, 1 << 18), threads, dtN, 1 << 15)}
+        except Exception as e:   # the baseline is reporting only; never fail the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+// bpe.cuh -- the BPE merge loop, one warp per distinct word (north_star step 3).
+//
+// Replaces tokenize.py:62-101 (bpe) and :270-278 (get_pairs) for words that the device word cache
+// has not seen yet, and :99-100,:120-121 (piece -> id).  The reference's round structure is kept
+// exactly: in every round take the lowest-rank pair among the CURRENT adjacent pairs, merge all of
+// its non-overlapping occurrences left to right, stop when no pair has a rank or one symbol is left.
+// Symbols are integer ids of the strings the reference would hold (host_tables.hpp).
+#pragma once
+#include "device_common.cuh"
+
+namespace gzt {
+
+static const int BPE_SMEM_SYMS = 128;        // words up to 128 bytes are merged in shared memory
+static const uint32_t CP_INVALID = 0xFFFFFFFEu;
+
+// UTF-8 bytes -> initial symbols (tokenize.py:63-64).  S needs room for `len` entries. Returns #symbols.
+__device__ __forceinline__ uint32_t bpe_symbols(const DevTables& T, const uint8_t* key, uint32_t len, uint32_t* S, int lane) {
+    uint32_t n = 0, last_fin = SYM_NONE;
+    for (uint32_t base = 0; base < len; base += 32) {
+        uint32_t j = base + lane;
+        uint32_t b = j < len ? key[j] : 0;
+        bool lead = j < len && (((b & 0xC0) != 0x80) || j == 0);
+        uint32_t m = __ballot_sync(FULL_MASK, lead);
+        uint32_t mid = SYM_NONE, fin = SYM_NONE;
+        if (lead) {
+            int expect = b < 0x80 ? 1 : (b & 0xE0) == 0xC0 ? 2 : (b & 0xF0) == 0xE0 ? 3 : (b & 0xF8) == 0xF0 ? 4 : 0;
+            uint32_t cp = expect == 1 ? b : expect == 2 ? (b & 0x1F) : expect == 3 ? (b & 0x0F) : (b & 0x07);
+            int got = 1;
+            for (uint32_t k = j + 1; k < len && got < 5; k++) {
+                uint32_t c = key[k];
+                if ((c & 0xC0) != 0x80) break;
+                cp = (cp << 6) | (c & 0x3F);
+                got++;
+            }
+            if (expect == 0 || got != expect) cp = CP_INVALID;
+            if (cp != CP_INVALID) cp_symbols(T, cp, &mid, &fin);
+            S[n + __popc(m & ((1u << lane) - 1))] = mid;
+        }
+        if (m) last_fin = __shfl_sync(FULL_MASK, fin, 31 - __clz(m));
+        n += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0 && n > 0) S[n - 1] = last_fin;   // the last code point carries "</w>"
+    __syncwarp();
+    return n;
+}
+
+// The merge rounds (tokenize.py:69-98) on S[0..n). Returns the new length.
+__device__ __forceinline__ uint32_t bpe_rounds(const DevTables& T, uint32_t* S, uint32_t n, int lane) {
+    while (n > 1) {
+        // ---- bigram = min(pairs, key=rank)  (:70-71)
+        uint32_t best = 0xFFFFFFFFu, ba = 0, bb = 0, bm = 0;
+        for (uint32_t base = 0; base + 1 < n; base += 32) {
+            uint32_t i = base + lane;
+            if (i + 1 < n) {
+                uint32_t a = S[i], b = S[i + 1], mg;
+                uint32_t r = pair_rank(T, a, b, &mg);
+                if (r < best) { best = r; ba = a; bb = b; bm = mg; }
+            }
+        }
+        uint32_t gbest = __reduce_min_sync(FULL_MASK, best);
+        if (gbest == 0xFFFFFFFFu) break;                       // `if bigram not in self.bpe_ranks: break` (:72-73)
+        int src = __ffs(__ballot_sync(FULL_MASK, best == gbest)) - 1;   // ranks are unique per pair
+        ba = __shfl_sync(FULL_MASK, ba, src);
+        bb = __shfl_sync(FULL_MASK, bb, src);
+        bm = __shfl_sync(FULL_MASK, bm, src);
+        // ---- merge every non-overlapping (first, second) scanning left to right (:75-92)
+        uint32_t out = 0, carry = 0;   // carry: element `base` was consumed by a merge selected at base-1
+        for (uint32_t base = 0; base < n; base += 32) {
+            uint32_t i = base + lane;
+            uint32_t a = i < n ? S[i] : SYM_NONE;
+            uint32_t b = i + 1 < n ? S[i + 1] : SYM_NONE;
+            bool match = (i + 1 < n) && a == ba && b == bb;
+            uint32_t m = __ballot_sync(FULL_MASK, match);
+            uint32_t sel;
+            if (ba == bb) {
+                // runs of equal symbols: greedy picks every second match from the run start (a a a -> aa a)
+                uint32_t below = ~m & ((1u << lane) - 1);
+                int start = below ? 32 - __clz(below) : 0;           // first index of the run of matches ending at me
+                bool odd = ((lane - start) & 1) != 0;
+                bool pick = match && ((start == 0 && carry) ? odd : !odd);
+                sel = __ballot_sync(FULL_MASK, pick);
+            } else {
+                sel = m;
+            }
+            uint32_t consumed = (sel << 1) | carry;
+            carry = sel >> 31;
+            uint32_t valid = (n - base >= 32) ? FULL_MASK : ((1u << (n - base)) - 1);
+            uint32_t keep = valid & ~consumed;
+            uint32_t v = ((sel >> lane) & 1) ? bm : a;
+            __syncwarp();                                            // all loads of this window done before stores
+            if ((keep >> lane) & 1) S[out + __popc(keep & ((1u << lane) - 1))] = v;
+            out += __popc(keep);
+        }
+        __syncwarp();
+        n = out;                                                     // `if len(word) == 1: break` (:95-96) via loop condition
+    }
+    return n;
+}
+
+// symbol -> vocab id: non-final symbols are looked up as S+"@@", the final one as S[:-4] (:99-100,:120-121)
+__device__ __forceinline__ int32_t sym_to_id(const DevTables& T, uint32_t s, bool final_sym) {
+    if (s == SYM_NONE) return T.unk;
+    return final_sym ? T.id_fin[s] : T.id_cont[s];
+}
+
+// One warp per pending cache slot.
+__global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
+    __shared__ uint32_t sm_sym[8][BPE_SMEM_SYMS];
+    __shared__ __align__(16) uint8_t sm_key[8][16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t npend = C.ctr[C_PENDING];
+    if (npend > C.pending_cap) npend = C.pending_cap;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib; w < npend; w += nwarps) {
+        Slot* s = &C.slots[C.pending[w]];
+        const uint32_t len = s->len;
+        const uint8_t* key;
+        if (len <= 16) {
+            if (lane == 0) { *reinterpret_cast<uint64_t*>(&sm_key[wib][0]) = s->k0; *reinterpret_cast<uint64_t*>(&sm_key[wib][8]) = s->k1; }
+            __syncwarp();
+            key = sm_key[wib];
+        } else {
+            key = C.key_arena + s->k0;
+        }
+        uint32_t* S;
+        uint32_t scratch_off = 0;
+        const bool big = len > (uint32_t)BPE_SMEM_SYMS;
+        if (big) {   // long word: work in place in the token arena (capacity reserved by the chunk guard)
+            if (lane == 0) scratch_off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)len);
+            scratch_off = __shfl_sync(FULL_MASK, scratch_off, 0);
+            S = C.tok_arena + scratch_off;
+        } else {
+            S = sm_sym[wib];
+        }
+        uint32_t n = bpe_symbols(T, key, len, S, lane);
+        n = bpe_rounds(T, S, n, lane);
+        uint32_t t0 = 0, t1 = 0;
+        if (n <= 2) {
+            if (lane == 0) {
+                t0 = (uint32_t)sym_to_id(T, S[0], n == 1);
+                if (n == 2) t1 = (uint32_t)sym_to_id(T, S[1], true);
+            }
+        } else {
+            uint32_t off = scratch_off;
+            if (!big) {
+                if (lane == 0) off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)n);
+                off = __shfl_sync(FULL_MASK, off, 0);
+            }
+            for (uint32_t i = lane; i < n; i += 32) {
+                uint32_t sym = S[i];
+                __syncwarp();
+                C.tok_arena[off + i] = (uint32_t)sym_to_id(T, sym, i == n - 1);
+            }
+            t0 = off;
+        }
+        __syncwarp();
+        if (lane == 0) { s->t0 = t0; s->t1 = t1; s->ntok = n; }
+        __syncwarp();
+    }
+}
+
+// Tokenize.bpe(token) helper (tokenize.py:62-101): one word in `word`, result = code points per piece.
+__global__ void k_bpe_single(DevTables T, const uint8_t* word, uint32_t len, uint32_t* scratch, uint32_t* piece_ncp, uint32_t* n_out) {
+    const int lane = threadIdx.x & 31;
+    uint32_t n = bpe_symbols(T, word, len, scratch, lane);
+    n = bpe_rounds(T, scratch, n, lane);
+    for (uint32_t i = lane; i < n; i += 32) piece_ncp[i] = scratch[i] == SYM_NONE ? 1u : T.sym_ncp[scratch[i]] - ((i == n - 1) ? 4u : 0u);
+    if (lane == 0) *n_out = n;
+}
+
+}  // namespace gzt

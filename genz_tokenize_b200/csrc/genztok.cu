@@ -1,0 +1,932 @@
+// genztok.cu -- C ABI (include/genztok.h) and host orchestration of the CUDA pipeline.
+//
+// Per chunk of documents the device runs
+//   k_cache_guard / k_cache_clear   make room in the word cache (reset when the worst case would not fit)
+//   k_rows<G, FIXED>                split + cache lookup + framing + pad/truncate + mask + token types
+//   k_bpe_pending                   BPE for the words that were new in this chunk
+//   k_rows<G, FIXED> (row list)     redo the rows that met a new word
+//   k_post_rows (row list)          rows with special ids inside the text (generic token types)
+// and for ragged results (no padding / no truncation / max_len None or <= 0)
+//   k_rows<COUNT> -> k_bpe_pending -> k_rows<COUNT> (row list) -> k_row_lens -> k_scan_i64
+//   -> k_rows<RAGGED> -> k_post_rows.
+// Decode is k_decode<false> (lengths) -> k_scan_i64 -> k_decode<true>.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/genztok.h"
+#include "bpe.cuh"
+#include "device_common.cuh"
+#include "encode.cuh"
+#include "host_tables.hpp"
+#include "post.cuh"
+
+using namespace gzt;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ProfEvent { int name; cudaEvent_t a, b; };
+
+struct DeviceCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    DevTables T{};
+    WordCache C{};
+    bool cache_ready = false;
+    std::vector<void*> table_allocs;
+    // chunk workspace
+    DevBuf text, toff, pair, poff;                // inputs
+    DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
+    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc;
+    DevBuf slots, key_arena, tok_arena, pending, ctr;
+    // profiling
+    bool profiling = false;
+    std::vector<ProfEvent> events;
+    std::vector<cudaEvent_t> free_events;
+};
+
+}  // namespace
+
+struct genztok {
+    HostTables H;
+    std::vector<DeviceCtx*> devs;
+    std::string err;
+    std::atomic<int64_t> launches{0};
+    std::mutex mu;                       // encode/decode calls are serialised per handle
+    // options
+    int64_t max_chunk_bytes = 64ll << 20;
+    int64_t chunk_rows = 1ll << 20;
+    int64_t force_group = 0;
+    std::vector<std::string> prof_names;
+    std::map<std::string, std::pair<int64_t, double>> prof_acc;
+    // pinned host pool
+    std::multimap<size_t, void*> host_pool;
+    size_t host_pool_bytes = 0;
+};
+
+namespace {
+
+int fail(genztok_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) return fail(h, GENZTOK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+int prof_name_id(genztok_t* h, const char* name) {
+    for (size_t i = 0; i < h->prof_names.size(); i++) if (h->prof_names[i] == name) return (int)i;
+    h->prof_names.push_back(name);
+    return (int)h->prof_names.size() - 1;
+}
+
+struct LaunchScope {   // counts the launch and, when profiling, brackets it with events on the stream
+    genztok_t* h; DeviceCtx* d; ProfEvent ev{}; bool on;
+    LaunchScope(genztok_t* h_, DeviceCtx* d_, const char* name) : h(h_), d(d_), on(d_->profiling) {
+        h->launches++;
+        if (on) {
+            ev.name = prof_name_id(h, name);
+            for (cudaEvent_t* e : {&ev.a, &ev.b}) {
+                if (!d->free_events.empty()) { *e = d->free_events.back(); d->free_events.pop_back(); }
+                else cudaEventCreate(e);
+            }
+            cudaEventRecord(ev.a, cur_stream);
+        }
+    }
+    ~LaunchScope() {
+        if (on) { cudaEventRecord(ev.b, cur_stream); d->events.push_back(ev); }
+    }
+    static thread_local cudaStream_t cur_stream;
+};
+thread_local cudaStream_t LaunchScope::cur_stream = nullptr;
+
+template <class T>
+cudaError_t upload(DeviceCtx* d, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    d->table_allocs.push_back(p);
+    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = reinterpret_cast<const T*>(p);
+    return e;
+}
+
+int init_device(genztok_t* h, DeviceCtx* d) {
+    CU(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, d->device));
+    d->sm_count = prop.multiProcessorCount;
+    d->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    const HostTables& H = h->H;
+    DevTables& T = d->T;
+    CU(upload(d, H.pair_slots, &T.pair));
+    T.pair_mask = H.pair_mask;
+    CU(upload(d, H.cp_slots, &T.cp));
+    T.cp_mask = H.cp_mask;
+    CU(upload(d, H.id_cont, &T.id_cont));
+    CU(upload(d, H.id_fin, &T.id_fin));
+    CU(upload(d, H.sym_ncp, &T.sym_ncp));
+    CU(upload(d, H.form_blob, &T.form_blob));
+    CU(upload(d, H.mid_off, &T.mid_off));
+    CU(upload(d, H.mid_len, &T.mid_len));
+    CU(upload(d, H.last_off, &T.last_off));
+    CU(upload(d, H.last_len, &T.last_len));
+    T.n_ids = (int32_t)H.n_ids;
+    T.pad = H.special_id[0]; T.bos = H.special_id[1]; T.eos = H.special_id[2]; T.msk = H.special_id[3]; T.unk = H.special_id[4];
+    T.specials_distinct = (T.pad != T.bos && T.pad != T.eos && T.bos != T.eos) ? 1 : 0;
+    return GENZTOK_OK;
+}
+
+uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
+int ensure_cache(genztok_t* h, DeviceCtx* d) {
+    if (d->cache_ready) return GENZTOK_OK;
+    const uint64_t B = (uint64_t)h->max_chunk_bytes;
+    const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
+    CU(d->slots.ensure(slots * sizeof(Slot)));
+    CU(d->key_arena.ensure(B + 64));
+    CU(d->tok_arena.ensure((B + 64) * 4));
+    CU(d->pending.ensure((B / 2 + 64) * 4));
+    CU(d->ctr.ensure(C_COUNT * 8));
+    CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), d->stream));
+    CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, d->stream));
+    WordCache& C = d->C;
+    C.slots = d->slots.as<Slot>(); C.mask = (uint32_t)(slots - 1);
+    C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + 64;
+    C.tok_arena = d->tok_arena.as<uint32_t>(); C.tok_cap = B + 64;
+    C.pending = d->pending.as<uint32_t>(); C.pending_cap = B / 2 + 64;
+    C.ctr = d->ctr.as<unsigned long long>();
+    d->cache_ready = true;
+    return GENZTOK_OK;
+}
+
+int pick_group(genztok_t* h, int64_t bytes_a, int64_t bytes_b, int64_t n) {
+    if (h->force_group) return (int)h->force_group;
+    int64_t avg = n > 0 ? std::max(bytes_a, bytes_b) / n : 0;
+    if (avg <= 36) return 2;
+    if (avg <= 100) return 4;
+    if (avg <= 230) return 8;
+    if (avg <= 500) return 16;
+    return 32;
+}
+
+template <int G, int MODE>
+int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
+    constexpr int D = 32 / G;
+    int wpb = 8;
+    auto smem_for = [&](int w) { return (size_t)w * 8 * 32 * 4 + (MODE == MODE_FIXED ? (size_t)w * D * (((size_t)A.W + 3) & ~(size_t)3) * 4 : 0); };
+    while (wpb > 1 && smem_for(wpb) > d->smem_optin) wpb >>= 1;
+    const size_t smem = smem_for(wpb);
+    if (smem > d->smem_optin) return fail(h, GENZTOK_E_LIMIT, "row of %d ids does not fit shared memory", A.W);
+    auto kern = k_rows<G, MODE>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    if (occ < 1) occ = 1;
+    int64_t tiles = (n_items_hint + D - 1) / D;
+    int64_t blocks = std::min<int64_t>((tiles + wpb - 1) / wpb, (int64_t)d->sm_count * occ);
+    if (blocks < 1) blocks = 1;
+    LaunchScope ls(h, d, name);
+    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(d->T, d->C, A);
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+template <int MODE>
+int launch_rows(genztok_t* h, DeviceCtx* d, int G, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_hint) {
+    switch (G) {
+        case 2: return launch_rows_t<2, MODE>(h, d, A, st, name, n_hint);
+        case 4: return launch_rows_t<4, MODE>(h, d, A, st, name, n_hint);
+        case 8: return launch_rows_t<8, MODE>(h, d, A, st, name, n_hint);
+        case 16: return launch_rows_t<16, MODE>(h, d, A, st, name, n_hint);
+        default: return launch_rows_t<32, MODE>(h, d, A, st, name, n_hint);
+    }
+}
+
+// Can the fixed-layout kernel stage rows of W ids?  (G = 32, one warp per block is the smallest footprint)
+bool fixed_fits(const DeviceCtx* d, int32_t W) { return (size_t)8 * 32 * 4 + (((size_t)W + 3) & ~(size_t)3) * 4 <= d->smem_optin; }
+int clamp_group_for_smem(const DeviceCtx* d, int G, int32_t W) {
+    // prefer >= 4 warps per block: raise G (fewer rows per warp) until the tile fits
+    while (G < 32 && (size_t)4 * 8 * 32 * 4 + (size_t)4 * (32 / G) * (((size_t)W + 3) & ~(size_t)3) * 4 > d->smem_optin) G <<= 1;
+    return G;
+}
+
+int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force) {
+    {
+        LaunchScope ls(h, d, "k_cache_guard");
+        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)chunk_bytes, force);
+    }
+    {
+        LaunchScope ls(h, d, "k_cache_clear");
+        k_cache_clear<<<d->sm_count * 4, 256, 0, st>>>(d->C);
+    }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+int launch_bpe(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
+    LaunchScope ls(h, d, "k_bpe_pending");
+    k_bpe_pending<<<d->sm_count * 4, 256, 0, st>>>(d->T, d->C);
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+int8_t eos_as_i8(const DeviceCtx* d) { return (d->T.eos >= 0 && d->T.eos <= 127) ? (int8_t)d->T.eos : (int8_t)GENZTOK_EOS_MARK; }
+
+// ---- fixed layout: everything already on the device ------------------------------------------------
+int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Side& a, const Side* b, int64_t n, int32_t W, uint32_t flags,
+                           const genztok_dev_planes_t& P) {
+    LaunchScope::cur_stream = st;
+    int rc = ensure_cache(h, d);
+    if (rc) return rc;
+    const int64_t bytes = a.nbytes + (b ? b->nbytes : 0);
+    if (bytes > h->max_chunk_bytes) return fail(h, GENZTOK_E_LIMIT, "chunk of %lld bytes exceeds max_chunk_bytes=%lld", (long long)bytes, (long long)h->max_chunk_bytes);
+    if (n <= 0) return GENZTOK_OK;
+    CU(d->redo.ensure((size_t)n * 4));
+    CU(d->fix.ensure((size_t)n * 4));
+    rc = launch_guard(h, d, st, bytes + 16, 0);
+    if (rc) return rc;
+    RowArgs A{};
+    A.a = a;
+    if (b) A.b = *b;
+    A.has_pair = b != nullptr;
+    A.n_rows = n; A.W = W; A.flags = flags;
+    A.ids = P.input_ids; A.mask = P.attention_mask;
+    A.tt = (flags & GENZTOK_WANT_TOKEN_TYPE) ? P.token_type_ids : nullptr;
+    A.seq = (flags & GENZTOK_WANT_SEQUENCE_ID) ? P.sequence_id : nullptr;
+    A.row_len = P.row_len; A.seq_len = P.seq_len; A.status = P.row_status;
+    A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>();
+    A.eos_i8 = eos_as_i8(d);
+    int G = clamp_group_for_smem(d, pick_group(h, a.nbytes, b ? b->nbytes : 0, n), W);
+    rc = launch_rows<MODE_FIXED>(h, d, G, A, st, "k_rows_fixed", n);
+    if (rc) return rc;
+    rc = launch_bpe(h, d, st);
+    if (rc) return rc;
+    RowArgs R = A;
+    R.row_list = d->redo.as<uint32_t>();
+    rc = launch_rows<MODE_FIXED>(h, d, G, R, st, "k_rows_fixed_redo", std::min<int64_t>(n, (int64_t)d->sm_count * 64));
+    if (rc) return rc;
+    if (b && (A.tt || A.seq || A.status || A.seq_len)) {
+        PostArgs Q{};
+        Q.ids = P.input_ids; Q.W = W; Q.n_rows = n; Q.row_list = d->fix.as<uint32_t>();
+        Q.has_pair = 1; Q.tt = A.tt; Q.seq = A.seq; Q.seq_len = P.seq_len; Q.status = P.row_status;
+        Q.has_max_len = 1; Q.max_len = W; Q.padding = 1; Q.truncation = 1; Q.eos_i8 = A.eos_i8;
+        LaunchScope ls(h, d, "k_post_rows_fix");
+        k_post_rows<<<d->sm_count, 256, 0, st>>>(d->T, Q, d->C.ctr + C_FIX);
+        CU(cudaGetLastError());
+    }
+    return GENZTOK_OK;
+}
+
+void* host_pool_get(genztok_t* h, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    auto it = h->host_pool.lower_bound(bytes);
+    if (it != h->host_pool.end() && it->first <= bytes + bytes / 4 + 4096) {
+        void* p = it->second;
+        h->host_pool_bytes -= it->first;
+        h->host_pool.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+struct OutBlock {
+    std::vector<std::pair<void*, size_t>> pinned;   // returned to the pool on free
+    std::vector<void*> mallocs;
+};
+
+template <class T>
+T* out_alloc(genztok_t* h, OutBlock* ob, size_t count) {
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    void* p = host_pool_get(h, bytes);
+    if (!p) return nullptr;
+    ob->pinned.push_back({p, bytes});
+    return reinterpret_cast<T*>(p);
+}
+
+struct Mode { bool fixed; bool has_max_len; int32_t max_len; int padding, truncation; };
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* genztok_version(void) { return "genztok-b200 0.1 (sm_100a)"; }
+
+const char* genztok_last_error(const genztok_t* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int genztok_create(const char* vocab_path, const char* bpe_path, const char* const specials_utf8[5], const int* device_ids, int n_devices,
+                   genztok_t** out) {
+    if (!vocab_path || !bpe_path || !out || n_devices < 0) return fail(nullptr, GENZTOK_E_INVALID, "genztok_create: bad arguments");
+    genztok_t* h = new genztok();
+    if (!h->H.build(vocab_path, bpe_path, specials_utf8)) {
+        g_create_err = h->H.err;
+        int code = h->H.err_code;
+        delete h;
+        return code;
+    }
+    for (int i = 0; i < n_devices; i++) {
+        DeviceCtx* d = new DeviceCtx();
+        d->device = device_ids ? device_ids[i] : i;
+        h->devs.push_back(d);
+        int rc = init_device(h, d);
+        if (rc) {
+            g_create_err = h->err;
+            genztok_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return GENZTOK_OK;
+}
+
+void genztok_destroy(genztok_t* h) {
+    if (!h) return;
+    for (DeviceCtx* d : h->devs) {
+        cudaSetDevice(d->device);
+        if (d->stream) cudaStreamSynchronize(d->stream);
+        for (void* p : d->table_allocs) cudaFree(p);
+        for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->slots,
+                          &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
+            b->release();
+        for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        for (auto e : d->free_events) cudaEventDestroy(e);
+        if (d->stream) cudaStreamDestroy(d->stream);
+        delete d;
+    }
+    for (auto& kv : h->host_pool) cudaFreeHost(kv.second);
+    delete h;
+}
+
+int64_t genztok_vocab_size(const genztok_t* h) { return (int64_t)h->H.enc_keys.size(); }
+int genztok_special_ids(const genztok_t* h, int32_t out[5]) {
+    for (int i = 0; i < 5; i++) out[i] = h->H.special_id[i];
+    return GENZTOK_OK;
+}
+int64_t genztok_encoder_count(const genztok_t* h) { return (int64_t)h->H.enc_keys.size(); }
+int genztok_encoder_entry(const genztok_t* h, int64_t i, const uint8_t** key, int64_t* key_len, int32_t* id) {
+    if (i < 0 || i >= (int64_t)h->H.enc_keys.size()) return GENZTOK_E_INVALID;
+    *key = (const uint8_t*)h->H.enc_keys[(size_t)i].data();
+    *key_len = (int64_t)h->H.enc_keys[(size_t)i].size();
+    *id = h->H.enc_vals[(size_t)i];
+    return GENZTOK_OK;
+}
+int32_t genztok_encoder_get(const genztok_t* h, const uint8_t* key, int64_t key_len) {
+    return h->H.enc_get(std::string((const char*)key, (size_t)key_len), -1);
+}
+int genztok_decoder_get(const genztok_t* h, int64_t id, const uint8_t** key, int64_t* key_len) {
+    *key = nullptr; *key_len = 0;
+    if (id < 0 || id >= h->H.n_ids || h->H.decoder[(size_t)id] < 0) return GENZTOK_OK;
+    const std::string& s = h->H.enc_keys[(size_t)h->H.decoder[(size_t)id]];
+    *key = (const uint8_t*)s.data(); *key_len = (int64_t)s.size();
+    return GENZTOK_OK;
+}
+int64_t genztok_merge_count(const genztok_t* h) { return (int64_t)h->H.merge_lines.size(); }
+int genztok_merge_line(const genztok_t* h, int64_t i, const uint8_t** line, int64_t* line_len) {
+    if (i < 0 || i >= (int64_t)h->H.merge_lines.size()) return GENZTOK_E_INVALID;
+    *line = (const uint8_t*)h->H.merge_lines[(size_t)i].data();
+    *line_len = (int64_t)h->H.merge_lines[(size_t)i].size();
+    return GENZTOK_OK;
+}
+int32_t genztok_rank_get(const genztok_t* h, const uint8_t* l, int64_t l_len, const uint8_t* r, int64_t r_len) {
+    return h->H.rank_get(std::string((const char*)l, (size_t)l_len), std::string((const char*)r, (size_t)r_len));
+}
+
+int genztok_device_count(const genztok_t* h) { return (int)h->devs.size(); }
+int64_t genztok_launch_count(const genztok_t* h) { return h->launches.load(); }
+
+void* genztok_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void genztok_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
+    std::string n = name ? name : "";
+    if (n == "max_chunk_bytes") {
+        for (DeviceCtx* d : h->devs) if (d->cache_ready) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes must be set before the first encode");
+        if (value < 4096) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes too small");
+        h->max_chunk_bytes = value;
+    } else if (n == "chunk_rows") {
+        if (value < 1) return fail(h, GENZTOK_E_INVALID, "chunk_rows < 1");
+        h->chunk_rows = value;
+    } else if (n == "group") {
+        if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32) return fail(h, GENZTOK_E_INVALID, "group must be 0,2,4,8,16,32");
+        h->force_group = value;
+    } else return fail(h, GENZTOK_E_INVALID, "unknown option %s", n.c_str());
+    return GENZTOK_OK;
+}
+
+int genztok_cache_reset(genztok_t* h) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (DeviceCtx* d : h->devs) {
+        if (!d->cache_ready) continue;
+        CU(cudaSetDevice(d->device));
+        LaunchScope::cur_stream = d->stream;
+        int rc = launch_guard(h, d, d->stream, 0, 1);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    return GENZTOK_OK;
+}
+
+int genztok_set_profiling(genztok_t* h, int on) {
+    for (DeviceCtx* d : h->devs) d->profiling = on != 0;
+    return GENZTOK_OK;
+}
+
+int64_t genztok_profile_report(genztok_t* h, char* buf, int64_t cap, int reset) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (DeviceCtx* d : h->devs) {
+        cudaSetDevice(d->device);
+        cudaDeviceSynchronize();
+        for (auto& e : d->events) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+                auto& acc = h->prof_acc[h->prof_names[(size_t)e.name]];
+                acc.first += 1; acc.second += ms;
+            } else cudaGetLastError();
+            d->free_events.push_back(e.a); d->free_events.push_back(e.b);
+        }
+        d->events.clear();
+    }
+    std::string s = "{";
+    bool first = true;
+    for (auto& kv : h->prof_acc) {
+        char t[256];
+        snprintf(t, sizeof t, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+        s += t; first = false;
+    }
+    s += "}";
+    if (reset) h->prof_acc.clear();
+    if (buf && cap > 0) { size_t n = std::min<size_t>(s.size(), (size_t)cap - 1); memcpy(buf, s.data(), n); buf[n] = 0; }
+    return (int64_t)s.size() + 1;
+}
+
+// ---- encode -----------------------------------------------------------------------------------------
+int genztok_encode_device(genztok_t* h, int dev, const uint8_t* d_text, const int64_t* d_text_off, int64_t text_bytes, const uint8_t* d_pair,
+                          const int64_t* d_pair_off, int64_t pair_bytes, int64_t n, int32_t max_len, uint32_t flags,
+                          const genztok_dev_planes_t* planes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d (handle has %d)", dev, (int)h->devs.size());
+    if (!planes || !planes->input_ids || n < 0 || !d_text_off || (text_bytes > 0 && !d_text)) return fail(h, GENZTOK_E_INVALID, "genztok_encode_device: bad arguments");
+    if (max_len < 1) return fail(h, GENZTOK_E_INVALID, "genztok_encode_device needs max_len >= 1 (fixed layout)");
+    if (((uintptr_t)d_text & 15) || ((uintptr_t)d_pair & 15)) return fail(h, GENZTOK_E_INVALID, "device text buffers must be 16-byte aligned");
+    if (flags & GENZTOK_WANT_SPANS) return fail(h, GENZTOK_E_INVALID, "spans are not available in the fixed device layout");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    if (!fixed_fits(d, max_len)) return fail(h, GENZTOK_E_LIMIT, "max_len=%d does not fit the fixed-layout kernel; use genztok_encode", max_len);
+    Side a{d_text, d_text_off, text_bytes}, b{d_pair, d_pair_off, pair_bytes};
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    return encode_fixed_on_device(h, d, st, a, d_pair_off ? &b : nullptr, n, max_len, flags, *planes);
+}
+
+void genztok_free_encoded(genztok_t* h, genztok_encoded_t* out) {
+    if (!out || !out->_owner) return;
+    OutBlock* ob = reinterpret_cast<OutBlock*>(out->_owner);
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        for (auto& pr : ob->pinned) {
+            if (h->host_pool_bytes + pr.second > (size_t)8 << 30) cudaFreeHost(pr.first);
+            else { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        }
+    }
+    for (void* p : ob->mallocs) free(p);
+    delete ob;
+    memset(out, 0, sizeof *out);
+}
+
+int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, const uint8_t* pair, const int64_t* pair_off, int64_t n,
+                   int32_t max_len, int padding, int truncation, uint32_t flags, genztok_encoded_t* out) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (!out || n < 0 || !text_off) return fail(h, GENZTOK_E_INVALID, "genztok_encode: bad arguments");
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    if (flags & GENZTOK_WANT_SPANS) return fail(h, GENZTOK_E_INVALID, "spans: not implemented yet");
+    memset(out, 0, sizeof *out);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[0];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    LaunchScope::cur_stream = st;
+    const bool has_pair = pair_off != nullptr;
+    const bool has_max_len = max_len != GENZTOK_MAX_LEN_NONE;
+    const bool fixed = has_max_len && max_len >= 1 && padding && truncation && fixed_fits(d, max_len);
+    const int8_t eos8 = eos_as_i8(d);
+    OutBlock* ob = new OutBlock();
+    out->_owner = ob;
+    out->n = n; out->has_pair = has_pair;
+    const bool want_tt = has_pair && (flags & GENZTOK_WANT_TOKEN_TYPE), want_seq = has_pair && (flags & GENZTOK_WANT_SEQUENCE_ID);
+
+#define OOM_CHECK(p) if (!(p)) { genztok_free_encoded_nolock(h, out); return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
+    auto genztok_free_encoded_nolock = [](genztok_t* hh, genztok_encoded_t* o) {
+        OutBlock* b = reinterpret_cast<OutBlock*>(o->_owner);
+        for (auto& pr : b->pinned) { hh->host_pool.insert({pr.second, pr.first}); hh->host_pool_bytes += pr.second; }
+        for (void* p : b->mallocs) free(p);
+        delete b;
+        memset(o, 0, sizeof *o);
+    };
+#define FAIL_RC(rc) { int _rc = (rc); if (_rc) { cudaStreamSynchronize(st); genztok_free_encoded_nolock(h, out); return _rc; } }
+#define CUF(call) { cudaError_t _e = (call); if (_e != cudaSuccess) { cudaStreamSynchronize(st); genztok_free_encoded_nolock(h, out); \
+        return fail(h, GENZTOK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); } }
+
+    // chunk boundaries: rows [r0, r1) with at most chunk_rows rows and max_chunk_bytes bytes
+    std::vector<int64_t> cuts{0};
+    {
+        int64_t r0 = 0;
+        while (r0 < n) {
+            int64_t r1 = std::min<int64_t>(n, r0 + h->chunk_rows);
+            auto bytes_of = [&](int64_t a, int64_t b) { return (text_off[b] - text_off[a]) + (has_pair ? pair_off[b] - pair_off[a] : 0) + 64; };
+            if (bytes_of(r0, r1) > h->max_chunk_bytes) {
+                int64_t lo = r0 + 1, hi = r1;   // largest r1 that fits (at least one row)
+                while (lo < hi) { int64_t mid = (lo + hi + 1) / 2; if (bytes_of(r0, mid) <= h->max_chunk_bytes) lo = mid; else hi = mid - 1; }
+                r1 = lo;
+                if (bytes_of(r0, r1) > h->max_chunk_bytes) {
+                    genztok_free_encoded_nolock(h, out);
+                    return fail(h, GENZTOK_E_LIMIT, "document %lld is larger than max_chunk_bytes=%lld", (long long)r0, (long long)h->max_chunk_bytes);
+                }
+            }
+            cuts.push_back(r1);
+            r0 = r1;
+        }
+    }
+    FAIL_RC(ensure_cache(h, d));
+
+    // ragged accumulators (host, pageable)
+    std::vector<int32_t> r_ids; std::vector<uint8_t> r_mask; std::vector<int8_t> r_tt, r_seq;
+    std::vector<int64_t> r_off;
+    if (fixed) {
+        const size_t tot = (size_t)n * (size_t)max_len;
+        out->width = max_len; out->total = (int64_t)tot;
+        out->input_ids = out_alloc<int32_t>(h, ob, tot); OOM_CHECK(out->input_ids);
+        out->attention_mask = out_alloc<uint8_t>(h, ob, tot); OOM_CHECK(out->attention_mask);
+        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
+        if (want_tt) { out->token_type_ids = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->token_type_ids); out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len); }
+        if (want_seq) { out->sequence_id = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->sequence_id); }
+        if (has_pair) { out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len); out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status); }
+    } else {
+        out->width = 0;
+        out->row_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->row_off);
+        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
+        if (has_pair) {
+            out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len);
+            out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len);
+            out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status);
+        }
+        out->row_off[0] = 0;
+    }
+    unsigned long long tokens_before = 0;
+    CUF(cudaMemcpyAsync(&tokens_before, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
+    CUF(cudaStreamSynchronize(st));
+
+    int64_t ragged_total = 0;
+    for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+        const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], m = r1 - r0;
+        const int64_t tb0 = text_off[r0], tb = text_off[r1] - tb0;
+        const int64_t pb0 = has_pair ? pair_off[r0] : 0, pb = has_pair ? pair_off[r1] - pb0 : 0;
+        // Offsets stay absolute (as in the caller's buffer): the chunk is copied to dev + (tb0 & 15) and the base
+        // pointer is shifted by -tb0, so that base + 16k is 16-byte aligned, as the kernel's LDG.128 needs.
+        const int64_t ta = tb0 & 15, pa = pb0 & 15;
+        CUF(d->text.ensure((size_t)tb + 96)); CUF(d->toff.ensure((size_t)(m + 1) * 8));
+        if (tb) CUF(cudaMemcpyAsync(d->text.as<uint8_t>() + ta, text + tb0, (size_t)tb, cudaMemcpyHostToDevice, st));
+        CUF(cudaMemcpyAsync(d->toff.p, text_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (has_pair) {
+            CUF(d->pair.ensure((size_t)pb + 96)); CUF(d->poff.ensure((size_t)(m + 1) * 8));
+            if (pb) CUF(cudaMemcpyAsync(d->pair.as<uint8_t>() + pa, pair + pb0, (size_t)pb, cudaMemcpyHostToDevice, st));
+            CUF(cudaMemcpyAsync(d->poff.p, pair_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+        }
+        Side a{d->text.as<uint8_t>() + ta - tb0, d->toff.as<int64_t>(), tb};
+        Side b{has_pair ? d->pair.as<uint8_t>() + pa - pb0 : nullptr, d->poff.as<int64_t>(), pb};
+
+        if (fixed) {
+            const size_t tot = (size_t)m * (size_t)max_len;
+            CUF(d->ids.ensure(tot * 4)); CUF(d->mask.ensure(tot)); CUF(d->row_len.ensure((size_t)m * 4));
+            genztok_dev_planes_t P{};
+            P.input_ids = d->ids.as<int32_t>(); P.attention_mask = d->mask.as<uint8_t>(); P.row_len = d->row_len.as<int32_t>();
+            if (want_tt) { CUF(d->tt.ensure(tot)); P.token_type_ids = d->tt.as<int8_t>(); }
+            if (want_seq) { CUF(d->seq.ensure(tot)); P.sequence_id = d->seq.as<int8_t>(); }
+            if (has_pair) { CUF(d->seq_len.ensure((size_t)m * 4)); CUF(d->status.ensure((size_t)m)); P.seq_len = d->seq_len.as<int32_t>(); P.row_status = d->status.as<uint8_t>(); }
+            FAIL_RC(encode_fixed_on_device(h, d, st, a, has_pair ? &b : nullptr, m, max_len, flags, P));
+            const size_t o0 = (size_t)r0 * (size_t)max_len;
+            CUF(cudaMemcpyAsync(out->input_ids + o0, d->ids.p, tot * 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(out->attention_mask + o0, d->mask.p, tot, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(out->row_len + r0, d->row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            if (want_tt) CUF(cudaMemcpyAsync(out->token_type_ids + o0, d->tt.p, tot, cudaMemcpyDeviceToHost, st));
+            if (want_seq) CUF(cudaMemcpyAsync(out->sequence_id + o0, d->seq.p, tot, cudaMemcpyDeviceToHost, st));
+            if (has_pair) {
+                CUF(cudaMemcpyAsync(out->seq_len + r0, d->seq_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+                CUF(cudaMemcpyAsync(out->row_status + r0, d->status.p, (size_t)m, cudaMemcpyDeviceToHost, st));
+            }
+            CUF(cudaStreamSynchronize(st));   // device buffers are reused by the next chunk
+            continue;
+        }
+
+        // ---- ragged layout ---------------------------------------------------------------------------
+        if (tb + pb + 16 > h->max_chunk_bytes) FAIL_RC(fail(h, GENZTOK_E_LIMIT, "chunk too large"));
+        CUF(d->redo.ensure((size_t)m * 4)); CUF(d->fix.ensure((size_t)m * 4));
+        CUF(d->L.ensure((size_t)m * 4)); CUF(d->keep.ensure((size_t)m * 4)); CUF(d->out_len.ensure((size_t)m * 8));
+        CUF(d->row_off.ensure((size_t)(m + 1) * 8)); CUF(d->tail.ensure((size_t)m));
+        FAIL_RC(launch_guard(h, d, st, tb + pb + 16, 0));
+        RowArgs A{};
+        A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = flags;
+        A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8;
+        const int G = pick_group(h, tb, pb, m);
+        FAIL_RC(launch_rows<MODE_COUNT>(h, d, G, A, st, "k_rows_count", m));
+        FAIL_RC(launch_bpe(h, d, st));
+        RowArgs R = A; R.row_list = d->redo.as<uint32_t>();
+        FAIL_RC(launch_rows<MODE_COUNT>(h, d, G, R, st, "k_rows_count_redo", std::min<int64_t>(m, (int64_t)d->sm_count * 64)));
+        LenArgs LA{d->L.as<int32_t>(), m, (int32_t)has_max_len, has_max_len ? max_len : 0, padding ? 1 : 0, truncation ? 1 : 0,
+                   d->keep.as<int32_t>(), d->out_len.as<int64_t>(), d->tail.as<uint8_t>()};
+        { LaunchScope ls(h, d, "k_row_lens"); k_row_lens<<<(unsigned)std::min<int64_t>((m + 255) / 256, 4096), 256, 0, st>>>(LA); }
+        { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), m); }
+        int64_t total = 0;
+        CUF(cudaMemcpyAsync(&total, d->row_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st));
+        CUF(cudaStreamSynchronize(st));
+        CUF(d->ids.ensure((size_t)total * 4 + 16)); CUF(d->mask.ensure((size_t)total + 16)); CUF(d->row_len.ensure((size_t)m * 4));
+        if (has_pair) { CUF(d->tt.ensure((size_t)total + 16)); CUF(d->seq.ensure((size_t)total + 16)); CUF(d->seq_len.ensure((size_t)m * 4)); CUF(d->tt_len.ensure((size_t)m * 4)); CUF(d->status.ensure((size_t)m)); }
+        { LaunchScope ls(h, d, "k_reset_lists"); k_reset_lists<<<1, 1, 0, st>>>(d->C); }
+        RowArgs E = A;
+        E.ids = d->ids.as<int32_t>(); E.row_off = d->row_off.as<int64_t>(); E.keep = d->keep.as<int32_t>();
+        FAIL_RC(launch_rows<MODE_RAGGED>(h, d, G, E, st, "k_rows_ragged", m));
+        PostArgs Q{};
+        Q.ids = d->ids.as<int32_t>(); Q.row_off = d->row_off.as<int64_t>(); Q.n_rows = m; Q.keep = d->keep.as<int32_t>(); Q.tail = d->tail.as<uint8_t>();
+        Q.mask = d->mask.as<uint8_t>(); Q.has_pair = has_pair; Q.row_len = d->row_len.as<int32_t>();
+        if (has_pair) { Q.tt = d->tt.as<int8_t>(); Q.seq = d->seq.as<int8_t>(); Q.tt_len = d->tt_len.as<int32_t>(); Q.seq_len = d->seq_len.as<int32_t>(); Q.status = d->status.as<uint8_t>(); }
+        Q.has_max_len = has_max_len; Q.max_len = has_max_len ? max_len : 0; Q.padding = padding ? 1 : 0; Q.truncation = truncation ? 1 : 0; Q.eos_i8 = eos8;
+        Q.tokens_ctr = d->C.ctr + C_TOKENS;
+        { LaunchScope ls(h, d, "k_post_rows"); k_post_rows<<<(unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->T, Q, nullptr); }
+        CUF(cudaGetLastError());
+        // bring the chunk home
+        const size_t old = r_ids.size();
+        r_ids.resize(old + (size_t)total); r_mask.resize(old + (size_t)total);
+        if (has_pair) { r_tt.resize(old + (size_t)total); r_seq.resize(old + (size_t)total); }
+        std::vector<int64_t> offs((size_t)m + 1);
+        if (total) {
+            CUF(cudaMemcpyAsync(r_ids.data() + old, d->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(r_mask.data() + old, d->mask.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            if (has_pair) {
+                CUF(cudaMemcpyAsync(r_tt.data() + old, d->tt.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+                CUF(cudaMemcpyAsync(r_seq.data() + old, d->seq.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        CUF(cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUF(cudaMemcpyAsync(out->row_len + r0, d->row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        if (has_pair) {
+            CUF(cudaMemcpyAsync(out->seq_len + r0, d->seq_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(out->tt_len + r0, d->tt_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(out->row_status + r0, d->status.p, (size_t)m, cudaMemcpyDeviceToHost, st));
+        }
+        CUF(cudaStreamSynchronize(st));
+        for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = ragged_total + offs[(size_t)i];
+        ragged_total += total;
+    }
+    unsigned long long tokens_after = 0, nerr = 0;
+    CUF(cudaMemcpyAsync(&tokens_after, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
+    CUF(cudaMemcpyAsync(&nerr, d->C.ctr + C_ERR, 8, cudaMemcpyDeviceToHost, st));
+    CUF(cudaStreamSynchronize(st));
+    if (nerr) FAIL_RC(fail(h, GENZTOK_E_CUDA, "internal error: device pipeline reported %llu inconsistencies", nerr));
+    out->real_tokens = (int64_t)(tokens_after - tokens_before);
+    if (fixed) {
+        if (want_tt) for (int64_t r = 0; r < n; r++) out->tt_len[r] = max_len;
+    } else {
+        out->total = ragged_total;
+        auto keepv = [&](auto& vec, auto** dst) {
+            using E = typename std::remove_reference<decltype(vec)>::type::value_type;
+            E* p = (E*)malloc(std::max<size_t>(vec.size() * sizeof(E), 16));
+            if (!vec.empty()) memcpy(p, vec.data(), vec.size() * sizeof(E));
+            ob->mallocs.push_back(p);
+            *dst = p;
+        };
+        keepv(r_ids, &out->input_ids); keepv(r_mask, &out->attention_mask);
+        if (has_pair) { keepv(r_tt, &out->token_type_ids); keepv(r_seq, &out->sequence_id); }
+    }
+    return GENZTOK_OK;
+#undef OOM_CHECK
+#undef FAIL_RC
+#undef CUF
+}
+
+// ---- decode -------------------------------------------------------------------------------------------
+int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                          uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_out_off || (!d_ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    LaunchScope::cur_stream = st;
+    DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes};
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 8));
+    if (!d_bytes) {
+        CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
+        A.out_len = d->out_len.as<int64_t>();
+        if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode<false><<<grid, 256, 0, st>>>(d->T, A); }
+        { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->out_len.as<int64_t>(), d_out_off, n); }
+        CU(cudaGetLastError());
+        if (total_bytes) {
+            CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return GENZTOK_OK;
+    }
+    if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode<true><<<grid, 256, 0, st>>>(d->T, A); }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+void genztok_free_text(genztok_t* h, genztok_text_t* out) {
+    if (!out || !out->_owner) return;
+    OutBlock* ob = reinterpret_cast<OutBlock*>(out->_owner);
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+    }
+    for (void* p : ob->mallocs) free(p);
+    delete ob;
+    memset(out, 0, sizeof *out);
+}
+
+int genztok_decode(genztok_t* h, const int32_t* ids, const int64_t* ids_off, int64_t n, int32_t width, genztok_text_t* out) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (!out || n < 0 || (!ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode: bad arguments");
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    memset(out, 0, sizeof *out);
+    DeviceCtx* d = h->devs[0];
+    OutBlock* ob = new OutBlock();
+    int64_t* off = nullptr; uint8_t* bytes = nullptr;
+    int rc = GENZTOK_OK;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        off = out_alloc<int64_t>(h, ob, (size_t)n + 1);
+    }
+    if (!off) { delete ob; return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
+    off[0] = 0;
+    const int64_t rows_per_chunk = std::max<int64_t>(1, h->chunk_rows);
+    std::vector<uint8_t> acc;
+    cudaSetDevice(d->device);
+    cudaStream_t st = d->stream;
+    int64_t total_all = 0;
+    for (int64_t r0 = 0; r0 < n && rc == GENZTOK_OK; r0 += rows_per_chunk) {
+        const int64_t r1 = std::min(n, r0 + rows_per_chunk), m = r1 - r0;
+        const int64_t i0 = ids_off ? ids_off[r0] : r0 * width, i1 = ids_off ? ids_off[r1] : r1 * width, ni = i1 - i0;
+        cudaError_t e;
+        if ((e = d->ids.ensure((size_t)ni * 4 + 16)) != cudaSuccess || (e = d->row_off.ensure((size_t)(m + 1) * 8)) != cudaSuccess ||
+            (e = d->toff.ensure((size_t)(m + 1) * 8)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        if (ni) cudaMemcpyAsync(d->ids.p, ids + i0, (size_t)ni * 4, cudaMemcpyHostToDevice, st);
+        const int64_t* d_ioff = nullptr;
+        if (ids_off) { cudaMemcpyAsync(d->toff.p, ids_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st); d_ioff = d->toff.as<int64_t>(); }
+        int64_t total = 0;
+        rc = genztok_decode_device(h, 0, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), nullptr, &total, st);
+        if (rc) break;
+        if ((e = d->text.ensure((size_t)total + 16)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        rc = genztok_decode_device(h, 0, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), d->text.as<uint8_t>(), nullptr, st);
+        if (rc) break;
+        std::vector<int64_t> offs((size_t)m + 1);
+        const size_t old = acc.size();
+        acc.resize(old + (size_t)total);
+        if (total) cudaMemcpyAsync(acc.data() + old, d->text.p, (size_t)total, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "decode: %s", cudaGetErrorString(e)); break; }
+        for (int64_t i = 1; i <= m; i++) off[r0 + i] = total_all + offs[(size_t)i];
+        total_all += total;
+    }
+    if (rc) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        delete ob;
+        return rc;
+    }
+    bytes = (uint8_t*)malloc(std::max<size_t>(acc.size(), 16));
+    if (!acc.empty()) memcpy(bytes, acc.data(), acc.size());
+    ob->mallocs.push_back(bytes);
+    out->n = n; out->total = total_all; out->bytes = bytes; out->off = off; out->_owner = ob;
+    return GENZTOK_OK;
+}
+
+// ---- helpers ----------------------------------------------------------------------------------------------
+int genztok_bpe_word(genztok_t* h, const uint8_t* word, int64_t word_len, int32_t* piece_cp, int64_t cap, int64_t* n_pieces) {
+    if (!h || !n_pieces || word_len < 0) return GENZTOK_E_INVALID;
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    *n_pieces = 0;
+    if (word_len == 0) return GENZTOK_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[0];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    LaunchScope::cur_stream = st;
+    const size_t L = (size_t)word_len;
+    CU(d->misc.ensure(L + 64 + (2 * L + 2) * 4));
+    uint8_t* dw = d->misc.as<uint8_t>();
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(dw + ((L + 63) & ~(size_t)63));
+    uint32_t* pieces = scratch + L;
+    uint32_t* dn = pieces + L;
+    CU(cudaMemcpyAsync(dw, word, L, cudaMemcpyHostToDevice, st));
+    { LaunchScope ls(h, d, "k_bpe_single"); k_bpe_single<<<1, 32, 0, st>>>(d->T, dw, (uint32_t)L, scratch, pieces, dn); }
+    CU(cudaGetLastError());
+    uint32_t nn = 0;
+    CU(cudaMemcpyAsync(&nn, dn, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_pieces = nn;
+    if ((int64_t)nn <= cap && piece_cp && nn) {
+        CU(cudaMemcpyAsync(piece_cp, pieces, (size_t)nn * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return GENZTOK_OK;
+}
+
+int genztok_sequence_id(genztok_t* h, const int32_t* ids, int64_t n, int apply_token_type, int8_t* out, int64_t* out_len, int* status) {
+    if (!h || n < 0 || !out_len || !status) return GENZTOK_E_INVALID;
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    *out_len = 0; *status = 0;
+    if (n == 0) { *status = apply_token_type ? 1 : 0; return GENZTOK_OK; }
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[0];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    LaunchScope::cur_stream = st;
+    CU(d->misc.ensure((size_t)n * 4 + (size_t)n + 64 + 16));
+    int32_t* dids = d->misc.as<int32_t>();
+    int8_t* dseq = reinterpret_cast<int8_t*>(dids + n);
+    int32_t* dlen = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(dids) + (((size_t)n * 5 + 15) & ~(size_t)15));
+    uint8_t* dstat = reinterpret_cast<uint8_t*>(dlen + 1);
+    CU(cudaMemcpyAsync(dids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    PostArgs Q{};
+    Q.ids = dids; Q.W = (int32_t)n; Q.n_rows = 1; Q.has_pair = 1; Q.seq = dseq; Q.seq_len = dlen; Q.status = dstat; Q.raw_seq = apply_token_type ? 0 : 1;
+    Q.eos_i8 = eos_as_i8(d);
+    { LaunchScope ls(h, d, "k_post_rows_helper"); k_post_rows<<<1, 32, 0, st>>>(d->T, Q, nullptr); }
+    CU(cudaGetLastError());
+    int32_t m = 0; uint8_t s8 = 0;
+    CU(cudaMemcpyAsync(&m, dlen, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&s8, dstat, 1, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_len = m; *status = s8;
+    if (out && m > 0) { CU(cudaMemcpyAsync(out, dseq, (size_t)m, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+    return GENZTOK_OK;
+}
+
+int genztok_attention_mask(genztok_t* h, const int32_t* ids, int64_t n, uint8_t* out) {
+    if (!h || n < 0) return GENZTOK_E_INVALID;
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    if (n == 0) return GENZTOK_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[0];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    LaunchScope::cur_stream = st;
+    CU(d->misc.ensure((size_t)n * 5 + 16));
+    int32_t* dids = d->misc.as<int32_t>();
+    uint8_t* dm = reinterpret_cast<uint8_t*>(dids + n);
+    CU(cudaMemcpyAsync(dids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    { LaunchScope ls(h, d, "k_mask_flat"); k_mask_flat<<<(unsigned)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, st>>>(dids, n, d->T.pad, dm); }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dm, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GENZTOK_OK;
+}
+
+}  // extern "C"

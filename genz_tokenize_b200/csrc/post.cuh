@@ -1,0 +1,243 @@
+// post.cuh -- generic per-row kernels: ragged-layout bookkeeping (row lengths, scan), and the
+// value-driven attention_mask / sequence_id / token_type_ids pass used for ragged rows, for rows
+// that contain special ids inside the text, and for the public helper methods.
+//
+//   k_row_lens     tokenize.py:141-146 (__padding) as lengths: what to keep, how long the row gets
+//   k_scan_i64     exclusive scan -> row offsets (north_star step 5)
+//   k_post_rows    tokenize.py:148-152 (mask), :163-182 (get_sequence_id), :154-161 (get_token_type),
+//                  :256-258 (token_type_ids padding), evaluated on the actual id values
+//   k_decode_*     tokenize.py:137-139 (decode) as a gather of precomputed per-id forms
+#pragma once
+#include "device_common.cuh"
+
+namespace gzt {
+
+struct LenArgs {
+    const int32_t* L;      // framed length per row
+    int64_t n_rows;
+    int32_t has_max_len, max_len, padding, truncation;
+    int32_t* keep;         // framed tokens copied
+    int64_t* out_len;      // final row length
+    uint8_t* tail;         // 0 none, 1 pad fill [keep, out_len), 2 eos at keep
+};
+
+__global__ void k_row_lens(LenArgs A) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t L = A.L[r];
+        int64_t keep = L, out = L; uint8_t tail = 0;
+        if (A.has_max_len && A.padding) {                       // tokenize.py:247
+            if (L < (int64_t)A.max_len) { out = A.max_len; tail = 1; }          // :142-143
+            else if (A.truncation) { keep = py_head(L, (int64_t)A.max_len - 1); out = keep + 1; tail = 2; }   // :144-145
+        }
+        A.keep[r] = (int32_t)keep; A.out_len[r] = out; A.tail[r] = tail;
+    }
+}
+
+// out[0..n] = exclusive scan of in[0..n) (out[n] = total). One block.
+__global__ void __launch_bounds__(1024) k_scan_i64(const int64_t* in, int64_t* out, int64_t n) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int64_t v = i < n ? in[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += t; }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int64_t s = warp_sums[lane], y = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(FULL_MASK, y, o); if (lane >= o) y += t; }
+            warp_sums[lane] = y - s;
+        }
+        __syncthreads();
+        const int64_t c = carry_s;
+        const int64_t incl = c + warp_sums[wid] + x;
+        if (i < n) out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+struct PostArgs {
+    int32_t* ids;              // flat
+    const int64_t* row_off;    // NULL -> fixed layout, row r at r*W
+    int32_t W;
+    int64_t n_rows;
+    const uint32_t* row_list;  // optional subset (count at ctr[C_FIX])
+    const int32_t* keep;       // with tail: fill [keep, len) first
+    const uint8_t* tail;
+    uint8_t* mask;             // may be NULL
+    int32_t has_pair;
+    int8_t* tt; int8_t* seq;   // row-aligned planes, may be NULL
+    int32_t* tt_len; int32_t* seq_len; uint8_t* status; int32_t* row_len;
+    int32_t has_max_len, max_len, padding, truncation;
+    int32_t raw_seq;           // 1: write get_sequence_id's result without get_token_type (helper API)
+    int8_t eos_i8;
+    unsigned long long* tokens_ctr;   // += sum(mask)
+};
+
+__global__ void __launch_bounds__(256) k_post_rows(DevTables T, PostArgs A, const unsigned long long* list_count) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_items = A.row_list ? *list_count : (uint64_t)A.n_rows;
+    unsigned long long tok_total = 0;
+    for (uint64_t it = warp; it < n_items; it += nwarps) {
+        const int64_t r = A.row_list ? (int64_t)A.row_list[it] : (int64_t)it;
+        const int64_t start = A.row_off ? A.row_off[r] : r * (int64_t)A.W;
+        const int32_t n = A.row_off ? (int32_t)(A.row_off[r + 1] - start) : A.W;
+        int32_t* Tk = A.ids + start;
+        if (A.tail) {                                               // tokenize.py:143 / :145
+            const int32_t kp = A.keep[r]; const uint8_t tl = A.tail[r];
+            if (tl == 1) for (int32_t i = kp + lane; i < n; i += 32) Tk[i] = T.pad;
+            else if (tl == 2 && lane == 0) Tk[kp] = T.eos;
+            __syncwarp();
+            if (A.row_len && lane == 0) A.row_len[r] = tl == 1 ? kp : n;
+        }
+        if (A.mask) {                                               // tokenize.py:148-152
+            int32_t cnt = 0;
+            for (int32_t i = lane; i < n; i += 32) { uint8_t on = Tk[i] != T.pad; A.mask[start + i] = on; cnt += on; }
+            cnt = __reduce_add_sync(FULL_MASK, cnt);
+            tok_total += (unsigned long long)cnt;
+        }
+        if (!A.has_pair) continue;
+        // ---- get_sequence_id (tokenize.py:163-182)
+        int32_t p1 = n;                                             // first </s>
+        for (int32_t base = 0; base < n && p1 == n; base += 32) {
+            const int32_t i = base + lane;
+            const uint32_t m = __ballot_sync(FULL_MASK, i < n && Tk[i] == T.eos);
+            if (m) p1 = base + __ffs(m) - 1;
+        }
+        int32_t e = -1;                                             // closing </s>: first i >= p1+2 with T[i]==eos and T[i-1]!=eos
+        for (int32_t base = p1 + 2; base < n && e < 0; base += 32) {
+            const int32_t i = base + lane;
+            const uint32_t m = __ballot_sync(FULL_MASK, i < n && Tk[i] == T.eos && Tk[i - 1] != T.eos);
+            if (m) e = base + __ffs(m) - 1;
+        }
+        const int32_t m_len = e >= 0 ? e + 1 : n;
+        // ---- get_token_type (tokenize.py:154-161): S[0]=0, S[-1]=1, first two remaining None -> 0, 1
+        int32_t f1 = -1, f2 = -1;
+        if (!A.raw_seq) {
+            for (int32_t base = 0; base < m_len && f2 < 0; base += 32) {
+                const int32_t i = base + lane;
+                bool none = false;
+                if (i < m_len && i != 0 && i != m_len - 1) {
+                    const int32_t t = Tk[i];
+                    none = (i < p1 && t == T.bos) || i == p1 || (i > p1 && t == T.eos);
+                }
+                uint32_t m = __ballot_sync(FULL_MASK, none);
+                if (m && f1 < 0) { f1 = base + __ffs(m) - 1; m &= m - 1; }
+                if (m && f2 < 0) f2 = base + __ffs(m) - 1;
+            }
+        }
+        const bool err = !A.raw_seq && (f2 < 0 || m_len == 0);
+        // token_type_ids length (tokenize.py:256-258)
+        int32_t tt_keep = m_len, tt_len = m_len; int tt_tail = 0;
+        if (A.has_max_len && A.padding) {
+            if (m_len < A.max_len) { tt_len = A.max_len; tt_tail = 1; }
+            else if (A.truncation) { tt_keep = (int32_t)py_head(m_len, (int64_t)A.max_len - 1); tt_len = tt_keep + 1; tt_tail = 2; }
+        }
+        const int32_t hi = n;
+        for (int32_t i = lane; i < hi; i += 32) {
+            int32_t v = -2;
+            if (i < m_len) {
+                const int32_t t = Tk[i];
+                const bool none = (i < p1 && t == T.bos) || i == p1 || (i > p1 && t == T.eos);
+                v = none ? -1 : (i < p1 ? 0 : 1);
+                if (!A.raw_seq) {
+                    if (i == f1) v = 0;
+                    if (i == f2) v = 1;
+                    if (i == 0) v = 0;
+                    if (i == m_len - 1) v = 1;
+                }
+            }
+            if (A.seq) A.seq[start + i] = (int8_t)v;
+            if (A.tt) {
+                int32_t tv = i < tt_keep ? v : (tt_tail == 2 && i == tt_keep ? (int32_t)A.eos_i8 : 0);
+                if (i < tt_len) A.tt[start + i] = (int8_t)tv;
+            }
+        }
+        if (lane == 0) {
+            if (A.seq_len) A.seq_len[r] = m_len;
+            if (A.tt_len) A.tt_len[r] = tt_len;
+            if (A.status) A.status[r] = err ? 1 : 0;
+        }
+    }
+    if (A.tokens_ctr && lane == 0 && tok_total) atomicAdd(A.tokens_ctr, tok_total);
+}
+
+// ---- decode (tokenize.py:137-139) ------------------------------------------------------------------
+struct DecArgs {
+    const int32_t* ids;
+    const int64_t* ids_off;   // NULL -> n rows of `width`
+    int32_t width;
+    int64_t n_rows;
+    int64_t* out_len;         // per row bytes (pass 1)
+    const int64_t* out_off;   // per row start (pass 2)
+    uint8_t* out;
+};
+
+__device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool last, uint32_t* off, uint32_t* len) {
+    const uint32_t k = (id >= 0 && id < T.n_ids) ? (uint32_t)id : (uint32_t)T.n_ids;   // decoder.get(i, unk_token)
+    *off = last ? T.last_off[k] : T.mid_off[k];
+    *len = last ? T.last_len[k] : T.mid_len[k];
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < (uint64_t)A.n_rows; r += nwarps) {
+        const int64_t start = A.ids_off ? A.ids_off[r] : (int64_t)r * A.width;
+        const int64_t n = A.ids_off ? A.ids_off[r + 1] - start : A.width;
+        const int32_t* ids = A.ids + start;
+        int64_t run = 0;
+        uint8_t* dst = WRITE ? A.out + A.out_off[r] : nullptr;
+        for (int64_t base = 0; base < n; base += 32) {
+            const int64_t i = base + lane;
+            uint32_t off = 0, len = 0;
+            if (i < n) dec_form(T, ids[i], i == n - 1, &off, &len);
+            uint32_t incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+            if (WRITE) {
+                uint8_t* d = dst + run + (incl - len);
+                const uint8_t* s = T.form_blob + off;
+                for (uint32_t k = 0; k < len; k++) d[k] = s[k];
+            }
+            run += __shfl_sync(FULL_MASK, incl, 31);
+        }
+        if (!WRITE && lane == 0) A.out_len[r] = run;
+    }
+}
+
+// get_atttention_mask helper on a flat id list
+__global__ void k_mask_flat(const int32_t* ids, int64_t n, int32_t pad, uint8_t* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = ids[i] != pad;
+}
+
+// ---- word cache housekeeping -------------------------------------------------------------------------
+// Decide whether the cache can take the worst case of the next chunk; if not, schedule a reset.
+__global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsigned long long need_keys, unsigned long long need_toks, int force) {
+    unsigned long long* c = C.ctr;
+    const unsigned long long cap = (unsigned long long)C.mask + 1;
+    const bool reset = force || (c[C_SLOTS] + need_slots) * 2 > cap || c[C_KEYS] + need_keys > C.key_cap || c[C_TOKS] + need_toks > C.tok_cap;
+    c[C_RESET] = reset;
+    if (reset) { c[C_SLOTS] = 0; c[C_KEYS] = 0; c[C_TOKS] = 0; }
+    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0;
+}
+__global__ void k_cache_clear(WordCache C) {
+    if (!C.ctr[C_RESET]) return;
+    uint4* p = reinterpret_cast<uint4*>(C.slots);
+    const uint64_t n = ((uint64_t)C.mask + 1) * 2;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = z;
+}
+__global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; }
+
+}  // namespace gzt

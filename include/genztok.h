@@ -1,0 +1,177 @@
+/*
+ * genztok.h -- C ABI of libgenztok.so, the B200-native encode/decode engine behind the
+ * `genz_tokenize.Tokenize` Python class.
+ *
+ * The reference (DVNghiem/genz-tokenize) has no FFI: its boundary is the public surface of
+ * `class Tokenize` (genz_tokenize/tokenize.py:6-267).  Each entry point below names the reference
+ * lines it replaces; the Python class in genz_tokenize_b200/tokenizer.py is a thin ctypes wrapper
+ * over exactly these symbols (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain C types only; strings are (pointer, length) pairs, never NUL-terminated ('\0' is a
+ *    legal word character, tokenize.py:106);
+ *  - text is UTF-8 (the 'surrogatepass' form of a Python str); documents are packed back to back
+ *    with int64 offsets[n+1];
+ *  - every function returns 0 or a negative GENZTOK_E_* code and never throws; the message is
+ *    available from genztok_last_error();
+ *  - all tokenisation work runs in CUDA kernels on the handle's device(s).  There is no CPU
+ *    fallback: a handle created with n_devices == 0 can only answer the table queries.
+ */
+#ifndef GENZTOK_H
+#define GENZTOK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENZTOK_OK 0
+#define GENZTOK_E_INVALID (-1)  /* bad argument */
+#define GENZTOK_E_IO (-2)       /* vocab / merges file cannot be opened (Python: FileNotFoundError) */
+#define GENZTOK_E_UTF8 (-3)     /* vocab / merges file is not valid UTF-8 (Python: UnicodeDecodeError) */
+#define GENZTOK_E_CUDA (-4)     /* CUDA runtime failure */
+#define GENZTOK_E_NOMEM (-5)
+#define GENZTOK_E_NODEVICE (-6) /* compute requested on a host-only handle */
+#define GENZTOK_E_LIMIT (-7)    /* batch exceeds an engine limit */
+
+/* `max_len` value meaning Python None (tokenize.py:187) */
+#define GENZTOK_MAX_LEN_NONE INT32_MIN
+
+/* `flags` of genztok_encode*: which optional planes to produce for sentence pairs */
+#define GENZTOK_WANT_TOKEN_TYPE 1u  /* token_type_ids (tokenize.py:254-258) */
+#define GENZTOK_WANT_SEQUENCE_ID 2u /* sequence_id    (tokenize.py:253-255) */
+#define GENZTOK_WANT_SPANS 4u       /* return_offset=True word->token spans (tokenize.py:105-117,225-234) */
+
+/* Entries of the int8 planes */
+#define GENZTOK_NONE (-1)      /* Python None */
+#define GENZTOK_EOS_MARK (-3)  /* "the </s> id" when that id does not fit an int8 (tokenize.py:145 via :257) */
+
+typedef struct genztok genztok_t;
+
+/* Result of an encode call.  All arrays are owned by the library (pinned host memory) until
+ * genztok_free_encoded().  Layout: row r occupies [row_start(r), row_start(r) + row_width(r)) of
+ * every flat plane, with row_start(r) = r*width when width > 0, else row_off[r].
+ * sequence_id / token_type_ids are row-aligned: only their first seq_len[r] / tt_len[r] entries
+ * are meaningful (the reference returns sequence_id unpadded, tokenize.py:253). */
+typedef struct genztok_encoded {
+    int64_t n;               /* rows */
+    int64_t total;           /* entries in each flat plane */
+    int32_t width;           /* > 0: fixed [n, width] layout (max_len >= 1, padding, truncation); 0: ragged */
+    int32_t has_pair;
+    int32_t *input_ids;      /* [total]  tokenize.py:250 */
+    uint8_t *attention_mask; /* [total]  tokenize.py:148-152,251 */
+    int64_t *row_off;        /* [n+1], NULL when width > 0 */
+    int32_t *row_len;        /* [n] tokens in the row before padding (framing included) */
+    int8_t *token_type_ids;  /* [total] or NULL */
+    int8_t *sequence_id;     /* [total] or NULL */
+    int32_t *tt_len;         /* [n] or NULL */
+    int32_t *seq_len;        /* [n] or NULL */
+    uint8_t *row_status;     /* [n] or NULL; 1 = the reference raises ValueError (tokenize.py:157-159) */
+    int64_t *span_off;       /* [n+1] entries of `spans` per row, or NULL */
+    int32_t *spans;          /* [span_off[n]][2] (first,last) token index pairs, or NULL */
+    int64_t real_tokens;     /* sum over rows of attention_mask */
+    void *_owner;            /* internal */
+} genztok_encoded_t;
+
+typedef struct genztok_text {
+    int64_t n;
+    int64_t total;    /* bytes */
+    uint8_t *bytes;   /* UTF-8, rows back to back */
+    int64_t *off;     /* [n+1] */
+    void *_owner;
+} genztok_text_t;
+
+/* Device-resident planes for genztok_encode_device (fixed layout only); any pointer may be NULL
+ * to skip that plane.  All are caller-allocated device memory on the handle's device. */
+typedef struct genztok_dev_planes {
+    int32_t *input_ids;      /* [n, max_len] */
+    uint8_t *attention_mask; /* [n, max_len] */
+    int8_t *token_type_ids;  /* [n, max_len] */
+    int8_t *sequence_id;     /* [n, max_len], entries past seq_len[r] are GENZTOK_NONE - 1 */
+    int32_t *row_len;        /* [n] */
+    int32_t *seq_len;        /* [n] */
+    uint8_t *row_status;     /* [n] */
+} genztok_dev_planes_t;
+
+/* ---- lifetime: Tokenize.__init__ / Tokenize.fromFile (tokenize.py:7-42, 261-267) ------------ */
+/* specials_utf8: pad,bos,eos,mask,unk strings (NULL or NULL entries = the reference defaults).
+ * device_ids/n_devices: CUDA ordinals to run on; n_devices == 0 builds the tables only. */
+int genztok_create(const char *vocab_path, const char *bpe_path, const char *const specials_utf8[5],
+                   const int *device_ids, int n_devices, genztok_t **out);
+void genztok_destroy(genztok_t *h);
+const char *genztok_last_error(const genztok_t *h); /* h may be NULL: last create() failure */
+const char *genztok_version(void);
+
+/* ---- table queries (host side; valid on any handle) ----------------------------------------- */
+int64_t genztok_vocab_size(const genztok_t *h);                 /* len(encoder), tokenize.py:59-60 */
+int genztok_special_ids(const genztok_t *h, int32_t out[5]);    /* encoder[pad|bos|eos|mask|unk] */
+/* encoder items in dict insertion order (tokenize.py:31-37,51) */
+int64_t genztok_encoder_count(const genztok_t *h);
+int genztok_encoder_entry(const genztok_t *h, int64_t i, const uint8_t **key, int64_t *key_len, int32_t *id);
+/* encoder.get(key) -> id or -1 */
+int32_t genztok_encoder_get(const genztok_t *h, const uint8_t *key, int64_t key_len);
+/* decoder.get(id) (tokenize.py:40): 0 and *key=NULL when absent */
+int genztok_decoder_get(const genztok_t *h, int64_t id, const uint8_t **key, int64_t *key_len);
+/* merge lines as read by add_bpe_file (tokenize.py:53-57): line i has rank i */
+int64_t genztok_merge_count(const genztok_t *h);
+int genztok_merge_line(const genztok_t *h, int64_t i, const uint8_t **line, int64_t *line_len);
+/* bpe_ranks.get((left,right)) -> rank or -1 */
+int32_t genztok_rank_get(const genztok_t *h, const uint8_t *l, int64_t l_len, const uint8_t *r, int64_t r_len);
+
+/* ---- encode: Tokenize.__call__ over a batch (tokenize.py:184-259) ---------------------------- */
+/* Host buffers in, pinned host buffers out.  pair == NULL means pair_text=None for every row.
+ * max_len == GENZTOK_MAX_LEN_NONE means None. */
+int genztok_encode(genztok_t *h, const uint8_t *text, const int64_t *text_off, const uint8_t *pair,
+                   const int64_t *pair_off, int64_t n, int32_t max_len, int padding, int truncation,
+                   uint32_t flags, genztok_encoded_t *out);
+void genztok_free_encoded(genztok_t *h, genztok_encoded_t *out);
+
+/* Device buffers in, device buffers out, on `stream` (a cudaStream_t, NULL = the handle's own
+ * stream) of device slot `dev` (index into device_ids).  Fixed layout only: requires
+ * max_len >= 1, padding and truncation.  Asynchronous: returns after enqueueing. */
+int genztok_encode_device(genztok_t *h, int dev, const uint8_t *d_text, const int64_t *d_text_off,
+                          int64_t text_bytes, const uint8_t *d_pair, const int64_t *d_pair_off,
+                          int64_t pair_bytes, int64_t n, int32_t max_len, uint32_t flags,
+                          const genztok_dev_planes_t *planes, void *stream);
+
+/* ---- decode: Tokenize.decode over a batch (tokenize.py:137-139) ------------------------------ */
+/* ids_off == NULL: n rows of `width` ids each.  Ids outside the decoder print the unk string. */
+int genztok_decode(genztok_t *h, const int32_t *ids, const int64_t *ids_off, int64_t n, int32_t width,
+                   genztok_text_t *out);
+void genztok_free_text(genztok_t *h, genztok_text_t *out);
+/* Device form: row byte lengths are produced first so that the caller can size `d_bytes`.
+ * Step 1 (d_bytes == NULL): fills d_out_off[n+1] and returns the total in *total_bytes (synchronises).
+ * Step 2: writes the text. */
+int genztok_decode_device(genztok_t *h, int dev, const int32_t *d_ids, const int64_t *d_ids_off, int64_t n,
+                          int32_t width, int64_t *d_out_off, uint8_t *d_bytes, int64_t *total_bytes, void *stream);
+
+/* ---- small public helpers of the class, also run on the device ------------------------------- */
+/* Tokenize.bpe(token) (tokenize.py:62-101): piece_cp[i] = code points in piece i of the word. */
+int genztok_bpe_word(genztok_t *h, const uint8_t *word, int64_t word_len, int32_t *piece_cp, int64_t cap,
+                     int64_t *n_pieces);
+/* get_sequence_id (tokenize.py:163-182), optionally followed by get_token_type (:154-161), on one
+ * id list.  out needs n entries (int8, GENZTOK_NONE = None).  *status = 1 when get_token_type raises. */
+int genztok_sequence_id(genztok_t *h, const int32_t *ids, int64_t n, int apply_token_type, int8_t *out,
+                        int64_t *out_len, int *status);
+/* get_atttention_mask (tokenize.py:148-152) */
+int genztok_attention_mask(genztok_t *h, const int32_t *ids, int64_t n, uint8_t *out);
+
+/* ---- utilities -------------------------------------------------------------------------------- */
+void *genztok_host_alloc(size_t bytes); /* pinned host memory for inputs */
+void genztok_host_free(void *p);
+int genztok_device_count(const genztok_t *h);
+int genztok_cache_reset(genztok_t *h);                    /* drop the device word cache */
+int64_t genztok_launch_count(const genztok_t *h);         /* kernels launched by this handle so far */
+/* Per-kernel CUDA-event timing (off by default).  The report is a JSON object
+ * {"kernel": {"launches": L, "ms": T}, ...}; returns the length needed. */
+int genztok_set_profiling(genztok_t *h, int on);
+int64_t genztok_profile_report(genztok_t *h, char *buf, int64_t cap, int reset);
+/* Engine knobs: "chunk_rows", "cache_slots_log2", ... */
+int genztok_set_option(genztok_t *h, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENZTOK_H */

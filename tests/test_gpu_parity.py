@@ -1,0 +1,238 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the reference-generated golden vectors and,
+on seeded synthetic batches, against the CPU oracle.  Bit-exact for every output (integer work)."""
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from golden_util import check_cases
+from parity_util import assert_matches_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tok():
+    from genz_tokenize_b200 import Tokenize
+    return Tokenize()
+
+
+def no_offset(cases):
+    return [c for c in cases if not c["kw"].get("return_offset")]
+
+
+def test_readme_vector(tok, golden):
+    check_cases(tok, golden["readme"], "readme")
+    assert tok.decode([1, 770, 2]) == "<s> sinh_viên </s>"
+    out = tok("sinh_viên công_nghệ", "hello", max_len=10, padding=True, truncation=True)
+    assert out["input_ids"] == [1, 770, 1444, 2, 2, 30469, 2, 0, 0, 0]
+    assert out["attention_mask"] == [1, 1, 1, 1, 1, 1, 1, 0, 0, 0]
+    assert out["sequence_id"] == [0, 0, 0, 0, 1, 1, 1]
+    assert out["token_type_ids"] == [0, 0, 0, 0, 1, 1, 1, 0, 0, 0]
+    assert tok("xin chào", text_pair="hello", max_len=8) == tok("xin chào", "hello", max_len=8)
+
+
+def test_corner_calls(tok, golden):
+    check_cases(tok, no_offset(golden["calls"]), "calls")
+
+
+def test_random_rows_single_calls(tok, golden):
+    for blk in golden["random"][:3]:
+        pairs = blk["pairs"] or [None] * len(blk["texts"])
+        cases = [{"text": t, "pair": p, "kw": blk["kw"], "out": o} for t, p, o in zip(blk["texts"], pairs, blk["out"])]
+        check_cases(tok, cases[:120], "random seed %d" % blk["gen"]["seed"])
+
+
+def test_random_rows_batch(tok, golden):
+    for blk in golden["random"]:
+        be = tok.encode_batch(blk["texts"], blk["pairs"], **blk["kw"])
+        for i, exp in enumerate(blk["out"]):
+            if "raises" in exp:
+                with pytest.raises(ValueError):
+                    be.row(i)
+            else:
+                assert be.row(i) == exp, (blk["gen"], i, blk["texts"][i], blk["pairs"][i] if blk["pairs"] else None)
+
+
+def test_bpe_strings(tok, golden):
+    for c in golden["bpe"]:
+        assert tok.bpe(c["w"]) == c["out"], c["w"]
+
+
+def test_sequence_id_state_machine(tok, golden):
+    for ids, raw, tt in golden["seqid"][::7]:
+        assert tok.get_sequence_id(ids) == raw, ids
+        if tt == "ValueError":
+            with pytest.raises(ValueError):
+                tok.get_token_type(tok.get_sequence_id(ids))
+        else:
+            assert tok.get_token_type(tok.get_sequence_id(ids)) == tt, ids
+            assert tok._sequence_id(ids, True) == tt, ids
+
+
+def test_attention_mask_helper(tok):
+    assert tok.get_atttention_mask([1, 5, 0, 2, 0, None, 7.0]) == [1, 1, 0, 1, 0, 1, 1]
+    assert tok.get_atttention_mask([]) == []
+
+
+def test_decode(tok, golden):
+    for c in golden["decode"]:
+        assert tok.decode(c["ids"]) == c["out"], c["ids"]
+    assert tok.decode(np.array([1, 770, 2])) == "<s> sinh_viên </s>"
+    assert tok.decode([1.0, 770.0, 2.5, None, "770"]) == "<s> sinh_viên <unk> <unk> <unk>"
+    rows = [c["ids"] for c in golden["decode"]]
+    off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    flat = np.array([v if -2**31 <= v < 2**31 else -1 for r in rows for v in r], dtype=np.int32)
+    assert tok.decode_batch(flat, off) == [c["out"] for c in golden["decode"]]
+
+
+def test_loader_quirks(golden):
+    from genz_tokenize_b200 import Tokenize
+    with tempfile.TemporaryDirectory() as td:
+        for i, L in enumerate(golden["loaders"]):
+            vp, mp = os.path.join(td, "v.txt"), os.path.join(td, "m.codes")
+            open(vp, "wb").write(L["vocab"].encode("utf-8"))
+            open(mp, "wb").write(L["merges"].encode("utf-8"))
+            t = Tokenize.fromFile(vp, mp)
+            t.set_option("max_chunk_bytes", 1 << 16)
+            assert t.vocab_size() == L["vocab_size"]
+            check_cases(t, L["calls"], "loader %d" % i)
+            for d in L["decode"]:
+                assert t.decode(d["ids"]) == d["out"], (i, d["ids"])
+
+
+def test_custom_specials(golden):
+    from genz_tokenize_b200 import Tokenize
+    cs = golden["custom_specials"]
+    t = Tokenize(*cs["specials"])
+    check_cases(t, cs["calls"], "custom specials")
+    for d in cs["decode"]:
+        assert t.decode(d["ids"]) == d["out"]
+
+
+def test_bpe_digest_all_vocab(tok, golden, oracle):
+    # every vocab word and merge concatenation, one word per document, against the oracle (which is pinned to the
+    # reference's digest in test_oracle_golden.py)
+    words = [w[:-2] if w.endswith("@@") else w for w in tok.encoder.keys()]
+    words += ["".join(k).replace("</w>", "") for k in tok.bpe_ranks.keys()]
+    words = [w for w in words if w and not any(c.isspace() for c in w)]
+    assert len(words) == golden["bpe_digest"]["n"]
+    be = tok.encode_batch(words)
+    orc = oracle.encode_batch(words, threads=8)
+    assert_matches_oracle(be, orc, what="all vocab words")
+
+
+CONFIGS = [
+    # seed, n, lo, hi, noise, paired, kw
+    (101, 3000, 3, 13, 0.0, False, dict(max_len=128)),
+    (102, 3000, 3, 13, 0.02, True, dict(max_len=256)),
+    (103, 2000, 0, 9, 0.2, True, dict(max_len=16)),
+    (104, 2000, 0, 9, 0.2, True, dict(max_len=7)),
+    (105, 2000, 0, 9, 0.2, False, dict(max_len=5)),
+    (106, 1500, 0, 9, 0.2, True, dict()),
+    (107, 1500, 0, 9, 0.2, True, dict(max_len=12, padding=False)),
+    (108, 1500, 0, 9, 0.2, True, dict(max_len=12, truncation=False)),
+    (109, 1500, 0, 9, 0.2, True, dict(max_len=0)),
+    (110, 1500, 0, 9, 0.2, True, dict(max_len=-2)),
+    (111, 1000, 0, 9, 0.2, False, dict(max_len=1)),
+    (112, 1000, 0, 9, 0.2, True, dict(max_len=2)),
+    (113, 600, 30, 120, 0.05, True, dict(max_len=100)),
+    (114, 300, 200, 900, 0.02, True, dict(max_len=512)),
+    (115, 1000, 3, 13, 0.05, True, dict(max_len=33)),      # width not a multiple of 16: scalar store path
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "seed%d" % c[0])
+def test_synthetic_vs_oracle(tok, oracle, cfg):
+    from genz_tokenize_b200 import workload
+    seed, n, lo, hi, noise, paired, kw = cfg
+    t = workload.generate(seed, n, lo, hi, noise)
+    p = workload.generate(seed + 5000, n, lo, hi, noise) if paired else None
+    be = tok.encode_batch(t, p, **kw)
+    orc = oracle.encode_batch(t, p, threads=8, **kw)
+    assert_matches_oracle(be, orc, what=str(cfg))
+
+
+@pytest.mark.parametrize("group", [2, 4, 8, 16, 32])
+def test_every_group_width_and_small_chunks(oracle, group):
+    # force each lanes-per-document variant of the row kernel, tiny chunks (many launches, cache resets)
+    from genz_tokenize_b200 import Tokenize, workload
+    tok = Tokenize()
+    tok.set_option("max_chunk_bytes", 1 << 15)
+    tok.set_option("chunk_rows", 257)
+    tok.set_option("group", group)
+    for seed, paired, kw in [(201, True, dict(max_len=24)), (202, False, dict(max_len=64)), (203, True, dict())]:
+        t = workload.generate(seed, 1500, 0, 20, 0.1)
+        p = workload.generate(seed + 5000, 1500, 0, 20, 0.1) if paired else None
+        be = tok.encode_batch(t, p, **kw)
+        orc = oracle.encode_batch(t, p, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="group %d seed %d" % (group, seed))
+
+
+def test_decode_roundtrip_batch(tok, oracle):
+    from genz_tokenize_b200 import workload
+    t = workload.generate(301, 4000, 3, 13, 0.02)
+    p = workload.generate(5301, 4000, 3, 13, 0.02)
+    be = tok.encode_batch(t, p, max_len=64)
+    texts = tok.decode_batch(be["input_ids"])
+    ref = oracle.decode_batch(be["input_ids"].reshape(-1), np.arange(0, 4000 * 64 + 1, 64, dtype=np.int64), threads=8)
+    assert texts == ref
+    rag = tok.encode_batch(t, p)
+    assert tok.decode_batch(rag["input_ids"], rag["row_off"]) == oracle.decode_batch(rag["input_ids"], rag["row_off"], threads=8)
+
+
+def test_device_api_matches_host_api(tok):
+    import torch
+    from genz_tokenize_b200 import workload
+    tb, to = workload.generate(401, 5000, 3, 13, 0.02)
+    pb, po = workload.generate(5401, 5000, 3, 13, 0.02)
+    host = tok.encode_batch((tb, to), (pb, po), max_len=96)
+    dev = torch.device("cuda:0")
+    pad16 = lambda a: torch.from_numpy(np.concatenate([a, np.zeros((-len(a)) % 16 + 16, dtype=np.uint8)])).to(dev)
+    out = tok.encode_device(pad16(tb), torch.from_numpy(to).to(dev), pad16(pb), torch.from_numpy(po).to(dev), max_len=96,
+                            token_type_ids=True, sequence_id=True, text_bytes=len(tb), pair_bytes=len(pb))
+    torch.cuda.synchronize()
+    assert np.array_equal(out["input_ids"].cpu().numpy(), host["input_ids"])
+    assert np.array_equal(out["attention_mask"].cpu().numpy(), host["attention_mask"])
+    assert np.array_equal(out["token_type_ids"].cpu().numpy(), host["token_type_ids"])
+    assert np.array_equal(out["row_status"].cpu().numpy(), host["row_status"])
+    assert np.array_equal(out["seq_len"].cpu().numpy(), host["seq_len"])
+    # DLPack hand-off of a result plane
+    cap = torch.utils.dlpack.to_dlpack(out["input_ids"])
+    again = torch.utils.dlpack.from_dlpack(cap)
+    assert again.data_ptr() == out["input_ids"].data_ptr()
+    # device decode
+    db, do = tok.decode_device(out["input_ids"])
+    texts = tok.decode_batch(host["input_ids"])
+    raw, off = db.cpu().numpy().tobytes(), do.cpu().numpy()
+    assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(5000)] == texts
+
+
+def test_config2_full_size_properties(tok, oracle):
+    # BASELINE.json configs[1]: 1M single sentences, max_len=128 -- first 100k rows against the oracle, the whole
+    # batch through size-independent properties (row framing, mask == non-pad, decode/encode idempotence on a sample)
+    from genz_tokenize_b200 import workload
+    t = workload.generate(1234, 1 << 20, 3, 13, 0.0)
+    be = tok.encode_batch(t, max_len=128)
+    ids, mask = be["input_ids"], be["attention_mask"]
+    assert ids.shape == (1 << 20, 128)
+    assert (ids[:, 0] == 1).all()
+    assert np.array_equal(mask, (ids != 0).astype(np.uint8))
+    rl = be["row_len"]
+    assert np.array_equal(rl, mask.sum(axis=1))
+    assert (ids[np.arange(len(rl)), rl - 1] == 2).all()
+    assert int(be["real_tokens"]) == int(mask.sum())
+    n = 100000
+    sub = (t[0][:t[1][n]], t[1][:n + 1])
+    orc = oracle.encode_batch(sub, None, max_len=128, threads=8)
+    assert np.array_equal(ids[:n].reshape(-1), orc["ids"])
+    # every word of W is one token: a row has exactly (#words + 2) real tokens
+    words = np.diff(np.searchsorted(np.nonzero(t[0] == 0x20)[0], t[1])) + (np.diff(t[1]) > 0)
+    assert np.array_equal(rl, np.minimum(words + 2, 128))
+    # checksum is independent of chunking
+    tok2 = type(tok)()
+    tok2.set_option("max_chunk_bytes", 1 << 22)
+    be2 = tok2.encode_batch((t[0][:t[1][200000]], t[1][:200001]), max_len=128)
+    assert hashlib.sha256(be2["input_ids"].tobytes()).hexdigest() == hashlib.sha256(ids[:200000].tobytes()).hexdigest()
