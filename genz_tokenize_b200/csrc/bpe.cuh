@@ -47,7 +47,7 @@ __device__ __forceinline__ uint32_t bpe_symbols(const DevTables& T, const uint8_
 
 // The merge rounds (tokenize.py:69-98) on S[0..n). Returns the new length.
 __device__ __forceinline__ uint32_t bpe_rounds(const DevTables& T, uint32_t* S, uint32_t n, int lane) {
-    while (n > 1) {
+    for (uint32_t round = 0, n0 = n; n > 1 && round <= n0; round++) {   // every round removes >= 1 symbol
         // ---- bigram = min(pairs, key=rank)  (:70-71)
         uint32_t best = 0xFFFFFFFFu, ba = 0, bb = 0, bm = 0;
         for (uint32_t base = 0; base + 1 < n; base += 32) {
@@ -147,11 +147,9 @@ __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
                 if (lane == 0) off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)n);
                 off = __shfl_sync(FULL_MASK, off, 0);
             }
-            for (uint32_t i = lane; i < n; i += 32) {
-                uint32_t sym = S[i];
-                __syncwarp();
-                C.tok_arena[off + i] = (uint32_t)sym_to_id(T, sym, i == n - 1);
-            }
+            // (for a long word S aliases tok_arena + off: each lane converts its own entries in place;
+            //  no warp-level sync may sit inside this loop, its trip count differs per lane)
+            for (uint32_t i = lane; i < n; i += 32) C.tok_arena[off + i] = (uint32_t)sym_to_id(T, S[i], i == n - 1);
             t0 = off;
         }
         __syncwarp();

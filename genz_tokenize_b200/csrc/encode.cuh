@@ -146,7 +146,8 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
                                                          uint32_t h) {
     uint32_t idx = h & C.mask;
     bool fresh = false;   // false: first look at a slot may come from L1
-    for (;;) {
+    for (uint32_t guard = 0;; guard++) {
+        if (guard > (1u << 24)) { atomicAdd(&C.ctr[C_ERR], 1ULL); return idx; }   // never spin forever: report instead
         Slot* s = &C.slots[idx];
         uint4 a = fresh ? ld_cg128(s) : *reinterpret_cast<const uint4*>(s);
         if (a.x == len) {

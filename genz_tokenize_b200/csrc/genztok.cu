@@ -120,6 +120,7 @@ struct LaunchScope {   // counts the launch and, when profiling, brackets it wit
     genztok_t* h; DeviceCtx* d; ProfEvent ev{}; bool on;
     LaunchScope(genztok_t* h_, DeviceCtx* d_, const char* name) : h(h_), d(d_), on(d_->profiling) {
         h->launches++;
+        dbg_name = name;
         if (on) {
             ev.name = prof_name_id(h, name);
             for (cudaEvent_t* e : {&ev.a, &ev.b}) {
@@ -131,7 +132,14 @@ struct LaunchScope {   // counts the launch and, when profiling, brackets it wit
     }
     ~LaunchScope() {
         if (on) { cudaEventRecord(ev.b, cur_stream); d->events.push_back(ev); }
+        static const bool debug = getenv("GENZTOK_DEBUG") != nullptr;
+        if (debug) {   // serialise and name every launch (hang / fault localisation)
+            cudaError_t e = cudaStreamSynchronize(cur_stream);
+            fprintf(stderr, "[genztok] %s: %s\n", dbg_name, cudaGetErrorString(e));
+            fflush(stderr);
+        }
     }
+    const char* dbg_name = "";
     static thread_local cudaStream_t cur_stream;
 };
 thread_local cudaStream_t LaunchScope::cur_stream = nullptr;

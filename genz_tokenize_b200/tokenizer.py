@@ -471,10 +471,17 @@ class Tokenize(object):
         slot = 0
         rc = self._lib.genztok_encode_device(self._h, slot, d_text.data_ptr(), d_text_off.data_ptr(), tbytes,
                                              d_pair.data_ptr() if has_pair else None, d_pair_off.data_ptr() if has_pair else None, pbytes,
-                                             n, int(max_len), flags, C.byref(P), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                                             n, int(max_len), flags, C.byref(P), self._torch_stream(dev))
         if rc:
             self._err(rc, "genztok_encode_device")
         return out
+
+    @staticmethod
+    def _torch_stream(dev):
+        """torch's current stream as a cudaStream_t; its default stream (handle 0) is the legacy stream, (cudaStream_t)1,
+        because the C ABI reads NULL as "the handle's own stream"."""
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream or 1)
 
     def decode_device(self, d_ids, d_ids_off=None):
         """Decode rows resident on the GPU: 2-D int32 tensor, or flat int32 + int64 offsets.  Returns (uint8 bytes, int64 offsets) tensors."""
@@ -488,7 +495,7 @@ class Tokenize(object):
             offp = d_ids_off.data_ptr()
         out_off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
         total = C.c_int64()
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        st = self._torch_stream(dev)
         rc = self._lib.genztok_decode_device(self._h, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
         if rc:
             self._err(rc, "genztok_decode_device")
