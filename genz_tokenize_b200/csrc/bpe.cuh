@@ -107,7 +107,7 @@ __device__ __forceinline__ int32_t sym_to_id(const DevTables& T, uint32_t s, boo
 // One warp per pending cache slot.
 __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
     __shared__ uint32_t sm_sym[8][BPE_SMEM_SYMS];
-    __shared__ __align__(16) uint8_t sm_key[8][16];
+    __shared__ __align__(16) uint8_t sm_key[8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t npend = C.ctr[C_PENDING];
     if (npend > C.pending_cap) npend = C.pending_cap;
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
         Slot* s = &C.slots[C.pending[w]];
         const uint32_t len = s->len;
         const uint8_t* key;
-        if (len <= 16) {
-            if (lane == 0) { *reinterpret_cast<uint64_t*>(&sm_key[wib][0]) = s->k0; *reinterpret_cast<uint64_t*>(&sm_key[wib][8]) = s->k1; }
+        if (len <= KEY_INLINE) {
+            if (lane < 3) reinterpret_cast<uint64_t*>(sm_key[wib])[lane] = lane == 0 ? s->k0 : lane == 1 ? s->k1 : s->k2;
             __syncwarp();
             key = sm_key[wib];
         } else {
@@ -126,34 +126,32 @@ __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
         uint32_t* S;
         uint32_t scratch_off = 0;
         const bool big = len > (uint32_t)BPE_SMEM_SYMS;
-        if (big) {   // long word: work in place in the token arena (capacity reserved by the chunk guard)
-            if (lane == 0) scratch_off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)len);
+        if (big) {   // long word: work in place in the token arena (capacity reserved by the chunk guard); entry 0 = count
+            if (lane == 0) scratch_off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)len + 1);
             scratch_off = __shfl_sync(FULL_MASK, scratch_off, 0);
-            S = C.tok_arena + scratch_off;
+            S = C.tok_arena + scratch_off + 1;
         } else {
             S = sm_sym[wib];
         }
         uint32_t n = bpe_symbols(T, key, len, S, lane);
         n = bpe_rounds(T, S, n, lane);
-        uint32_t t0 = 0, t1 = 0;
-        if (n <= 2) {
-            if (lane == 0) {
-                t0 = (uint32_t)sym_to_id(T, S[0], n == 1);
-                if (n == 2) t1 = (uint32_t)sym_to_id(T, S[1], true);
-            }
+        uint32_t val;
+        if (n == 1) {
+            val = VAL_SINGLE | ((uint32_t)sym_to_id(T, S[0], true) & VAL_PAYLOAD);
         } else {
             uint32_t off = scratch_off;
             if (!big) {
-                if (lane == 0) off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)n);
+                if (lane == 0) off = (uint32_t)atomicAdd(&C.ctr[C_TOKS], (unsigned long long)n + 1);
                 off = __shfl_sync(FULL_MASK, off, 0);
             }
-            // (for a long word S aliases tok_arena + off: each lane converts its own entries in place;
+            // (for a long word S aliases tok_arena + off + 1: each lane converts its own entries in place;
             //  no warp-level sync may sit inside this loop, its trip count differs per lane)
-            for (uint32_t i = lane; i < n; i += 32) C.tok_arena[off + i] = (uint32_t)sym_to_id(T, S[i], i == n - 1);
-            t0 = off;
+            for (uint32_t i = lane; i < n; i += 32) C.tok_arena[off + 1 + i] = (uint32_t)sym_to_id(T, S[i], i == n - 1);
+            if (lane == 0) C.tok_arena[off] = n;
+            val = VAL_MULTI | off;
         }
         __syncwarp();
-        if (lane == 0) { s->t0 = t0; s->t1 = t1; s->ntok = n; }
+        if (lane == 0) s->val = val;
         __syncwarp();
     }
 }

@@ -34,14 +34,15 @@ struct DevTables {
 // ------------------------------------------------------------------------------------------------
 struct __align__(32) Slot {
     uint32_t len;    // key length in bytes; SLOT_EMPTY / SLOT_LOCKED are states
-    uint32_t ntok;   // 0 = BPE pending
-    uint32_t t0;     // ntok <= 2: first token; else offset into tok_arena
-    uint32_t t1;     // ntok == 2: second token
-    uint64_t k0;     // len <= 16: key bytes 0..7 (zero padded); else offset into key_arena
-    uint64_t k1;     // len <= 16: key bytes 8..15;              else 64-bit hash of the key
+    uint32_t val;    // VAL_PENDING | VAL_SINGLE|id | VAL_MULTI|offset into tok_arena (arena[off] = n, then n ids)
+    uint64_t k0;     // len <= 24: key bytes 0..7 (zero padded); else offset into key_arena
+    uint64_t k1;     // len <= 24: key bytes 8..15;              else 64-bit hash of the key
+    uint64_t k2;     // len <= 24: key bytes 16..23;             else 0
 };
 static const uint32_t SLOT_EMPTY = 0u;
 static const uint32_t SLOT_LOCKED = 0xFFFFFFFFu;
+static const uint32_t KEY_INLINE = 24;
+static const uint32_t VAL_PENDING = 0u, VAL_SINGLE = 1u << 30, VAL_MULTI = 2u << 30, VAL_KIND = 3u << 30, VAL_PAYLOAD = (1u << 30) - 1;
 
 enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_COUNT = 16 };
 
@@ -83,23 +84,31 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
 }
-// murmur3-style hash of a <=16-byte key held in two 64-bit registers
-__device__ __forceinline__ uint32_t hash_key16(uint64_t k0, uint64_t k1, uint32_t len) {
+// Hash of a <=24-byte zero-padded key held in three 64-bit registers: multiply-xor per 32-bit word, then a
+// murmur finaliser.  (Every lookup verifies the full key, so quality only affects probe length.)
+__device__ __forceinline__ uint32_t hash_key24(uint64_t k0, uint64_t k1, uint64_t k2, uint32_t len) {
     uint32_t h = len * 0x9E3779B1u;
-    uint32_t w[4] = {(uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32)};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t k = w[i] * 0xcc9e2d51u;
-        k = rotl32(k, 15) * 0x1b873593u;
-        h ^= k;
-        h = rotl32(h, 13) * 5u + 0xe6546b64u;
-    }
+    h ^= (uint32_t)k0 * 0xcc9e2d51u;
+    h ^= (uint32_t)(k0 >> 32) * 0x1b873593u;
+    h ^= (uint32_t)k1 * 0x85ebca6bu;
+    h ^= (uint32_t)(k1 >> 32) * 0xc2b2ae35u;
+    h ^= (uint32_t)k2 * 0x27d4eb2fu;
+    h ^= (uint32_t)(k2 >> 32) * 0x165667b1u;
     return fmix32(h);
 }
+// 64-bit hash of a long key, 8 bytes at a time (unaligned bytes gathered bytewise only for the tail)
 __device__ __forceinline__ uint64_t hash_long(const uint8_t* p, uint32_t len) {
-    uint64_t h = 0xcbf29ce484222325ULL;
-    for (uint32_t i = 0; i < len; i++) { h ^= p[i]; h *= 0x100000001b3ULL; }
-    return h;
+    uint64_t h = 0xcbf29ce484222325ULL ^ len;
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v |= (uint64_t)p[i + k] << (8 * k);
+        h = (h ^ v) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    for (; i < len; i++) { h ^= p[i]; h *= 0x100000001b3ULL; }
+    return h ^ (h >> 32);
 }
 
 // (symL,symR) -> rank, merged.  Returns 0xFFFFFFFF when the pair has no rank.

@@ -2,7 +2,7 @@
 // truncation, padding, attention_mask and token types, one launch per chunk of documents.
 //
 // Replaces, per document (file:line in /root/reference/genz_tokenize/tokenize.py):
-//   :106      re.findall(r"\S+\n?", text)                 -> classify16 / scan_side
+//   :106      re.findall(r"\S+\n?", text)                 -> classify16 + word list
 //   :108-114  per-word bpe() + split                      -> word-cache hit (bpe.cuh fills misses)
 //   :120-121  piece -> id with <unk> fallback             -> stored in the cache slot
 //   :126-135  [bos] + ids + [eos]                         -> positions 0 / 1+nA
@@ -11,10 +11,13 @@
 //   :148-152  get_atttention_mask
 //   :154-182  get_sequence_id + get_token_type, :252-258 token_type_ids
 //
-// Work decomposition: a warp owns a tile of D = 32/G consecutive documents; G lanes walk one
-// document in 16-byte pieces (one LDG.128 per lane), the D token rows are staged in shared memory
-// and then written by the whole warp with 16-byte streaming stores.  Rows whose words are not all
-// in the cache yet are queued for a second pass after k_bpe_pending has filled the new slots.
+// Work decomposition.  A warp owns a TILE of D consecutive documents; their bytes are contiguous in the
+// packed batch, so the warp streams them as one byte range in windows of 30x16 bytes (+2 look-ahead
+// pieces): every lane classifies one 16-byte piece (LDG.128), word starts are compacted into a
+// shared-memory word list, and then all 32 lanes look up one word each (key gather, hash, one 32-byte
+// cache slot).  A segmented warp scan over (document, token count) gives every word its position in its
+// row; the D rows are staged in shared memory and written with 16-byte streaming stores by the whole warp.
+// Rows that met a word whose BPE is still pending are queued for a second pass (k_bpe_pending in between).
 #pragma once
 #include "device_common.cuh"
 
@@ -23,7 +26,7 @@ namespace gzt {
 enum RowMode { MODE_FIXED = 0, MODE_COUNT = 1, MODE_RAGGED = 2 };
 
 struct Side {
-    const uint8_t* bytes;   // 16-byte aligned, readable up to round_up(nbytes, 16)
+    const uint8_t* bytes;   // 16-byte aligned, readable up to round_up(nbytes, 16) + 16
     const int64_t* off;     // [n+1]
     int64_t nbytes;
 };
@@ -33,6 +36,7 @@ struct RowArgs {
     int32_t has_pair;
     int64_t n_rows;
     int32_t W;                 // FIXED: max_len
+    int32_t D;                 // documents per tile (1..32)
     uint32_t flags;
     // FIXED outputs
     int32_t* ids; uint8_t* mask; int8_t* tt; int8_t* seq;
@@ -48,6 +52,26 @@ struct RowArgs {
     int8_t eos_i8;
 };
 
+static const int WIN_LANES = 30;            // pieces whose word starts a window handles; 2 more are look-ahead
+static const int WLIST_CAP = WIN_LANES * 8; // at most 8 word starts per 16-byte piece
+static const uint32_t F_DIRTY = 1u, F_SPECIAL = 2u, F_PADTOK = 4u;
+
+// get_sequence_id + get_token_type in closed form for one row (see seq_describe)
+struct SeqDesc { int32_t p1, m, f1, f2, r1, r2, err; };
+
+// per-warp shared memory (the D token rows follow for MODE_FIXED)
+struct __align__(16) TileSmem {
+    int64_t doff[33];          // document offsets of the tile for the side being walked
+    int64_t dout[32];          // RAGGED: row start in ids
+    int32_t dpos[32];          // next token position per document
+    int32_t dnA[32];           // tokens of side A per document
+    uint32_t dflag[32];        // F_*
+    int32_t dkeep[32];         // RAGGED: tokens to keep
+    uint32_t bnd[32];          // document-start bits per piece of the current window
+    SeqDesc dsd[32];           // FIXED pairs: token-type description per row
+    uint16_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown)
+};
+
 // ---- byte classification -----------------------------------------------------------------------
 // bit i of the result = high bit of byte i of x (x has only 0x80 bits set)
 __device__ __forceinline__ uint32_t gather_msb(uint32_t x) { return (((x >> 7) * 0x00204081u) >> 21) & 0xFu; }
@@ -60,6 +84,12 @@ __device__ __forceinline__ uint32_t ascii_ws4(uint32_t w) {
     uint32_t ge1c = lo + 0x64646464u;   // >= 0x1C
     uint32_t ge21 = lo + 0x5F5F5F5Fu;   // >= 0x21
     return ((ge09 & ~ge0e) | (ge1c & ~ge21)) & ~w & 0x80808080u;
+}
+// bytes that can start a non-ASCII whitespace code point: 0xC2, 0xE1, 0xE2, 0xE3 -> 0x80 flags
+__device__ __forceinline__ uint32_t ws_lead4(uint32_t w) {
+    uint32_t lo = w & 0x7F7F7F7Fu;                // 0xC2 -> 0x42, 0xE1..0xE3 -> 0x61..0x63
+    uint32_t ge42 = lo + 0x3E3E3E3Eu, ge43 = lo + 0x3D3D3D3Du, ge61 = lo + 0x1F1F1F1Fu, ge64 = lo + 0x1C1C1C1Cu;
+    return ((ge42 & ~ge43) | (ge61 & ~ge64)) & w & 0x80808080u;
 }
 
 __device__ __forceinline__ uint32_t byte_of(const uint4& w, int j) {
@@ -83,25 +113,34 @@ __device__ __forceinline__ int multibyte_ws(uint32_t b0, const uint8_t* bytes, i
     return 0;
 }
 
+// index of the document that holds byte position p: largest k in [0, nd) with doff[k] <= p
+__device__ __forceinline__ int doc_of(const int64_t* doff, int nd, int64_t p) {
+    int lo = 0, hi = nd - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (doff[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // Whitespace bits of the 16 bytes at `a` (bits 0..15) plus spill into the next piece (bits 16,17).
-// Bytes outside [s,e) count as whitespace.
-__device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* bytes, int64_t a, int64_t s, int64_t e) {
+// Bytes outside [S,E) count as whitespace; a multi-byte whitespace never straddles two documents.
+__device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* bytes, int64_t a, int64_t S, int64_t E, const int64_t* doff, int nd) {
     uint32_t inseg = 0xFFFFu;
-    if (a < s) inseg &= 0xFFFFu << (int)(s - a);
-    if (a + 16 > e) inseg &= 0xFFFFu >> (int)(a + 16 - e);
+    if (a < S) inseg &= 0xFFFFu << (int)(S - a);
+    if (a + 16 > E) inseg &= 0xFFFFu >> (int)(a + 16 - E);
     uint32_t ws = gather_msb(ascii_ws4(w.x)) | (gather_msb(ascii_ws4(w.y)) << 4) | (gather_msb(ascii_ws4(w.z)) << 8) |
                   (gather_msb(ascii_ws4(w.w)) << 12);
-    // lead bytes >= 0xC0: bit7 & bit6
-    uint32_t lead = gather_msb(w.x & (w.x << 1) & 0x80808080u) | (gather_msb(w.y & (w.y << 1) & 0x80808080u) << 4) |
-                    (gather_msb(w.z & (w.z << 1) & 0x80808080u) << 8) | (gather_msb(w.w & (w.w << 1) & 0x80808080u) << 12);
-    lead &= inseg;
-    while (lead) {
-        int j = __ffs(lead) - 1;
-        lead &= lead - 1;
-        uint32_t b0 = byte_of(w, j);
-        if (b0 != 0xC2 && (b0 < 0xE1 || b0 > 0xE3)) continue;
-        int l = multibyte_ws(b0, bytes, a + j, e);
-        if (l) ws |= ((1u << l) - 1) << j;
+    if ((w.x | w.y | w.z | w.w) & 0x80808080u) {
+        uint32_t lead = gather_msb(ws_lead4(w.x)) | (gather_msb(ws_lead4(w.y)) << 4) | (gather_msb(ws_lead4(w.z)) << 8) |
+                        (gather_msb(ws_lead4(w.w)) << 12);
+        lead &= inseg;
+        while (lead) {
+            const int j = __ffs(lead) - 1;
+            lead &= lead - 1;
+            const int l = multibyte_ws(byte_of(w, j), bytes, a + j, E);
+            if (l && a + j + l <= doff[doc_of(doff, nd, a + j) + 1]) ws |= ((1u << l) - 1) << j;
+        }
     }
     return (ws & 0x3FFFFu) | (~inseg & 0xFFFFu);
 }
@@ -118,71 +157,79 @@ __device__ __noinline__ int64_t slow_word_end(const uint8_t* bytes, int64_t q, i
 }
 
 // ---- word -> cache slot --------------------------------------------------------------------------
-// 16-byte zero-padded key of the word at [p, p+len), len <= 16, via aligned 16-byte loads.
-__device__ __forceinline__ void load_key16(const uint8_t* bytes, int64_t p, uint32_t len, uint64_t* k0, uint64_t* k1) {
-    int64_t A = p & ~(int64_t)15;
+// 24-byte zero-padded key of the word at [p, p+len), len <= 24, via aligned 16-byte loads.
+__device__ __forceinline__ void load_key24(const uint8_t* bytes, int64_t p, uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    const int64_t A = p & ~(int64_t)15;
     int sh = (int)(p - A);
-    uint4 lo = ldg128(bytes + A);
-    uint64_t q0 = ((uint64_t)lo.y << 32) | lo.x, q1 = ((uint64_t)lo.w << 32) | lo.z, q2 = 0, q3 = 0;
-    if (sh + (int)len > 16) {
-        uint4 hi = ldg128(bytes + A + 16);
-        q2 = ((uint64_t)hi.y << 32) | hi.x;
-        q3 = ((uint64_t)hi.w << 32) | hi.z;
+    const int need = sh + (int)len;
+    uint4 v0 = ldg128(bytes + A);
+    uint64_t q0 = ((uint64_t)v0.y << 32) | v0.x, q1 = ((uint64_t)v0.w << 32) | v0.z, q2 = 0, q3 = 0, q4 = 0;
+    if (need > 16) {
+        uint4 v1 = ldg128(bytes + A + 16);
+        q2 = ((uint64_t)v1.y << 32) | v1.x;
+        q3 = ((uint64_t)v1.w << 32) | v1.z;
+        if (need > 32) {
+            uint2 v2 = __ldg(reinterpret_cast<const uint2*>(bytes + A + 32));
+            q4 = ((uint64_t)v2.y << 32) | v2.x;
+        }
     }
-    if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; sh -= 8; }
-    uint64_t r0 = q0, r1 = q1;
+    if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; sh -= 8; }
+    uint64_t r0 = q0, r1 = q1, r2 = q2;
     if (sh) {
-        int s8 = sh * 8;
+        const int s8 = sh * 8;
         r0 = (q0 >> s8) | (q1 << (64 - s8));
         r1 = (q1 >> s8) | (q2 << (64 - s8));
+        r2 = (q2 >> s8) | (q3 << (64 - s8));
     }
-    if (len < 8) { r0 &= (1ULL << (len * 8)) - 1; r1 = 0; }
-    else if (len < 16) { r1 &= (1ULL << ((len - 8) * 8)) - 1; }
-    *k0 = r0; *k1 = r1;
+    if (len <= 8) { if (len < 8) r0 &= (1ULL << (len * 8)) - 1; r1 = 0; r2 = 0; }
+    else if (len <= 16) { if (len < 16) r1 &= (1ULL << ((len - 8) * 8)) - 1; r2 = 0; }
+    else if (len < 24) r2 &= (1ULL << ((len - 16) * 8)) - 1;
+    *k0 = r0; *k1 = r1; *k2 = r2;
 }
 
-// Find the word in the cache or insert it (BPE pending).  Returns the slot index.
+__device__ __noinline__ bool long_key_equal(const uint8_t* kp, const uint8_t* wptr, uint32_t len) {
+    for (uint32_t i = 0; i < len; i++) if (kp[i] != wptr[i]) return false;
+    return true;
+}
+
+// Find the word in the cache or insert it (BPE pending).  Returns the slot's value word (VAL_*).
+// With insert_ok == false (second passes) an absent word is reported as VAL_PENDING and nothing is written.
 __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, const uint8_t* wptr, uint32_t len, uint64_t k0, uint64_t k1,
-                                                         uint32_t h) {
+                                                         uint64_t k2, uint32_t h, bool insert_ok) {
     uint32_t idx = h & C.mask;
-    bool fresh = false;   // false: first look at a slot may come from L1
+    bool fresh = false;   // false: the first look at a slot may be served by L1
     for (uint32_t guard = 0;; guard++) {
-        if (guard > (1u << 24)) { atomicAdd(&C.ctr[C_ERR], 1ULL); return idx; }   // never spin forever: report instead
+        if (guard > (1u << 24)) { atomicAdd(&C.ctr[C_ERR], 1ULL); return VAL_PENDING; }   // never spin forever: report instead
         Slot* s = &C.slots[idx];
-        uint4 a = fresh ? ld_cg128(s) : *reinterpret_cast<const uint4*>(s);
+        const uint4 a = fresh ? ld_cg128(s) : *reinterpret_cast<const uint4*>(s);
         if (a.x == len) {
-            uint4 b = fresh ? ld_cg128(reinterpret_cast<const uint4*>(s) + 1) : *(reinterpret_cast<const uint4*>(s) + 1);
-            uint64_t s0 = ((uint64_t)b.y << 32) | b.x, s1 = ((uint64_t)b.w << 32) | b.z;
+            const uint4 b = fresh ? ld_cg128(reinterpret_cast<const uint4*>(s) + 1) : *(reinterpret_cast<const uint4*>(s) + 1);
+            const uint64_t s0 = ((uint64_t)a.w << 32) | a.z, s1 = ((uint64_t)b.y << 32) | b.x, s2 = ((uint64_t)b.w << 32) | b.z;
             bool eq;
-            if (len <= 16) eq = (s0 == k0) && (s1 == k1);
-            else {
-                eq = s1 == k1;
-                if (eq) {
-                    const uint8_t* kp = C.key_arena + s0;
-                    for (uint32_t i = 0; i < len && eq; i++) eq = kp[i] == wptr[i];
-                }
-            }
-            if (eq) return idx;
+            if (len <= KEY_INLINE) eq = (s0 == k0) & (s1 == k1) & (s2 == k2);
+            else eq = s1 == k1 && long_key_equal(C.key_arena + s0, wptr, len);
+            if (eq) return a.y;
         } else if (a.x == SLOT_EMPTY || a.x == SLOT_LOCKED) {
             if (!fresh) { fresh = true; continue; }          // L1 may be stale: look again in L2
             if (a.x == SLOT_LOCKED) continue;                // another thread is writing this slot
-            uint32_t old = atomicCAS(&s->len, SLOT_EMPTY, SLOT_LOCKED);
+            if (!insert_ok) return VAL_PENDING;
+            const uint32_t old = atomicCAS(&s->len, SLOT_EMPTY, SLOT_LOCKED);
             if (old != SLOT_EMPTY) continue;                 // lost the race: re-examine the same slot
-            uint64_t v0 = k0, v1 = k1;
-            if (len > 16) {
-                uint64_t off = atomicAdd(&C.ctr[C_KEYS], (unsigned long long)len);
+            uint64_t v0 = k0;
+            if (len > KEY_INLINE) {
+                const uint64_t off = atomicAdd(&C.ctr[C_KEYS], (unsigned long long)len);
                 uint8_t* kp = C.key_arena + off;
                 for (uint32_t i = 0; i < len; i++) kp[i] = wptr[i];
                 v0 = off;
             }
-            s->ntok = 0; s->t0 = 0; s->t1 = 0; s->k0 = v0; s->k1 = v1;
+            s->val = VAL_PENDING; s->k0 = v0; s->k1 = k1; s->k2 = k2;
             __threadfence();
             st_release_u32(&s->len, len);
             atomicAdd(&C.ctr[C_SLOTS], 1ULL);
-            uint64_t pi = atomicAdd(&C.ctr[C_PENDING], 1ULL);
+            const uint64_t pi = atomicAdd(&C.ctr[C_PENDING], 1ULL);
             if (pi < C.pending_cap) C.pending[pi] = idx;
             else atomicAdd(&C.ctr[C_ERR], 1ULL);
-            return idx;
+            return VAL_PENDING;
         }
         idx = (idx + 1) & C.mask;
         fresh = false;
@@ -192,28 +239,28 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
 // ---- token types for a pair row in closed form ---------------------------------------------------
 // get_sequence_id + get_token_type (tokenize.py:154-182) evaluated on the known positions of
 // </s> in a row without interior special ids.  Generic rows go to k_post_rows.
-struct SeqDesc { int32_t p1, m, f1, f2, r1, r2, err; };
-
 __device__ __forceinline__ SeqDesc seq_describe(int32_t nA, int32_t L, int32_t W) {
     // eos positions of the final row T (length W): framed a, a+1, c=L-1 if they survive truncation, W-1 if truncated
-    int32_t E[4]; int ne = 0;
+    int32_t E0 = -1, E1 = -1, E2 = -1, E3 = -1; int ne = 0;
     const int32_t a = 1 + nA, c = L - 1;
-    const bool trunc = L >= W;
-    if (a <= W - 2) E[ne++] = a;
-    if (a + 1 <= W - 2) E[ne++] = a + 1;
-    if (c <= W - 2 && c > a + 1) E[ne++] = c;
-    if (trunc) E[ne++] = W - 1;
+    auto push = [&](int32_t v) { if (ne == 0) E0 = v; else if (ne == 1) E1 = v; else if (ne == 2) E2 = v; else E3 = v; ne++; };
+    if (a <= W - 2) push(a);
+    if (a + 1 <= W - 2) push(a + 1);
+    if (c <= W - 2 && c > a + 1) push(c);
+    if (L >= W) push(W - 1);
     SeqDesc d;
-    d.p1 = E[0];
+    d.p1 = E0;
     int32_t e = -1;
-    for (int k = 1; k < ne; k++)
-        if (E[k] >= d.p1 + 2 && E[k - 1] != E[k] - 1) { e = E[k]; break; }
+    if (ne > 1 && E1 >= d.p1 + 2 && E0 != E1 - 1) e = E1;
+    else if (ne > 2 && E2 >= d.p1 + 2 && E1 != E2 - 1) e = E2;
+    else if (ne > 3 && E3 >= d.p1 + 2 && E2 != E3 - 1) e = E3;
     d.m = e >= 0 ? e + 1 : W;
-    int32_t N[4]; int nn = 0;   // None positions after S[0]=0, S[m-1]=1
-    for (int k = 0; k < ne; k++)
-        if (E[k] < d.m && E[k] != 0 && E[k] != d.m - 1) N[nn++] = E[k];
-    d.f1 = nn > 0 ? N[0] : -1; d.f2 = nn > 1 ? N[1] : -1;
-    d.r1 = nn > 2 ? N[2] : -1; d.r2 = nn > 3 ? N[3] : -1;
+    int32_t N0 = -1, N1 = -1, N2 = -1, N3 = -1; int nn = 0;   // None positions after S[0]=0, S[m-1]=1
+    auto pushn = [&](int32_t v) {
+        if (v >= 0 && v < d.m && v != 0 && v != d.m - 1) { if (nn == 0) N0 = v; else if (nn == 1) N1 = v; else if (nn == 2) N2 = v; else N3 = v; nn++; }
+    };
+    pushn(E0); pushn(E1); pushn(E2); pushn(E3);
+    d.f1 = N0; d.f2 = N1; d.r1 = N2; d.r2 = N3;
     d.err = nn < 2;
     return d;
 }
@@ -226,253 +273,303 @@ __device__ __forceinline__ int32_t seq_value(const SeqDesc& d, int32_t i) {
     if (i == d.m - 1) v = 1;
     return v;
 }
-
-// ---- the row kernel --------------------------------------------------------------------------------
-template <int G, int MODE>
-struct RowKernel {
-    static constexpr int D = 32 / G;
-    static constexpr int MAXW = 8;   // word starts per 16-byte piece
-
-    // Walk one side of the tile's documents.  All 32 lanes call this; lanes [g*G, g*G+G) own document g.
-    // pos (group-uniform) is the next token position of the row; tokens at positions < limit are delivered.
-    __device__ static __forceinline__ void scan_side(const DevTables& T, const WordCache& C, const Side& sd, int64_t s, int64_t e, bool active,
-                                                    int gl, uint32_t* scratch /*[MAXW][32] for this warp*/, int lane, int32_t& pos, int32_t limit,
-                                                    uint32_t& flags, int32_t* rowbuf, int32_t* gout, int32_t glimit) {
-        const uint8_t* bytes = sd.bytes;
-        const int64_t base = s & ~(int64_t)15;
-        int32_t n_it = (active && e > s) ? (int32_t)((e - base + 16 * G - 1) / (16 * G)) : 0;
-        const int32_t max_it = __reduce_max_sync(FULL_MASK, n_it);
-        uint32_t carry = 1u << 15;    // the byte before the document is whitespace, nothing spills in
-        for (int32_t it = 0; it < max_it; ++it) {
-            const bool g_on = it < n_it && pos < limit;
-            const int64_t a = base + ((int64_t)it * G + gl) * 16;
-            const bool l_on = g_on && a < e;
-            uint32_t ws18 = 0xFFFFu;
-            if (l_on) {
-                uint4 w = ldg128(bytes + a);
-                ws18 = classify16(w, bytes, a, s, e);
-            }
-            uint32_t prev = __shfl_up_sync(FULL_MASK, ws18, 1, G);
-            if (gl == 0) prev = carry;
-            carry = __shfl_sync(FULL_MASK, ws18, G - 1, G);
-            const uint32_t nw = ~(ws18 | (prev >> 16)) & 0xFFFFu;
-            uint32_t st = nw & ~((nw << 1) | ((~prev >> 15) & 1u));
-            // non-whitespace bits of the following pieces, to find word ends without touching memory
-            uint64_t win = nw;
-            {
-                uint32_t n1 = __shfl_down_sync(FULL_MASK, nw, 1, G), n2 = __shfl_down_sync(FULL_MASK, nw, 2, G),
-                         n3 = __shfl_down_sync(FULL_MASK, nw, 3, G);
-                if (gl + 1 < G) win |= (uint64_t)n1 << 16;
-                if (gl + 2 < G) win |= (uint64_t)n2 << 32;
-                if (gl + 3 < G) win |= (uint64_t)n3 << 48;
-            }
-            const int known = 16 * ((G - gl) < 4 ? (G - gl) : 4);
-            // ---- my word starts: find end, look up
-            int32_t cnt = 0; int nwords = 0;
-            if (!l_on) st = 0;
-            while (st) {
-                const int b = __ffs(st) - 1;
-                st &= st - 1;
-                const int64_t p = a + b;
-                uint64_t z = (~win) >> (b + 1);
-                int run = z ? __ffsll((long long)z) : 65;     // bytes after p up to the first whitespace
-                int64_t end;
-                if (b + run < known) end = p + run;
-                else end = slow_word_end(bytes, a + known, e);
-                if (end < e && bytes[end] == 0x0A) end++;          // \S+\n?  (tokenize.py:106)
-                const uint32_t len = (uint32_t)(end - p);
-                uint64_t k0, k1; uint32_t h;
-                if (len <= 16) { load_key16(bytes, p, len, &k0, &k1); h = hash_key16(k0, k1, len); }
-                else { k1 = hash_long(bytes + p, len); k0 = 0; h = fmix32((uint32_t)k1 ^ (uint32_t)(k1 >> 32)); }
-                const uint32_t si = cache_find_or_insert(C, bytes + p, len, k0, k1, h);
-                const Slot* sl = &C.slots[si];
-                const uint32_t nt = sl->ntok;
-                uint32_t enc = si;
-                if (nt == 1) enc = 0x80000000u | sl->t0;
-                else if (nt == 0) flags |= 1u;                      // BPE pending: the row needs the second pass
-                cnt += (int32_t)nt;
-                if (nwords < MAXW) scratch[nwords * 32 + lane] = enc;
-                nwords++;
-            }
-            // ---- positions: exclusive scan of token counts over the group
-            int32_t incl = cnt;
+// token_type_ids / sequence_id bytes for positions i0..i0+3 of a fixed-width row
+__device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t W, int8_t eos_i8, uint32_t* ttw, uint32_t* sqw) {
+    const int32_t hi = i0 + 3;
+    auto in4 = [&](int32_t v) { return v >= i0 && v <= hi; };
+    if (i0 >= d.m) { *ttw = 0; *sqw = 0xFEFEFEFEu; return; }
+    if (hi < d.m && !(in4(0) | in4(d.m - 1) | in4(d.f1) | in4(d.f2) | in4(d.r1) | in4(d.r2) | in4(d.p1))) {
+        const uint32_t v = i0 < d.p1 ? 0u : 0x01010101u;
+        *ttw = v; *sqw = v;
+        return;
+    }
+    uint32_t t = 0, s = 0;
 #pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                int32_t t = __shfl_up_sync(FULL_MASK, incl, o, G);
-                if (gl >= o) incl += t;
+    for (int k = 0; k < 4; k++) {
+        const int32_t i = i0 + k;
+        const int32_t sv = i < d.m ? seq_value(d, i) : 0;
+        const int32_t tv = (d.m == W && i == W - 1) ? (int32_t)eos_i8 : sv;
+        t |= ((uint32_t)tv & 0xFFu) << (8 * k);
+        s |= ((uint32_t)(i < d.m ? sv : -2) & 0xFFu) << (8 * k);
+    }
+    *ttw = t; *sqw = s;
+}
+
+// ---- walking one side of a tile --------------------------------------------------------------------
+// All 32 lanes call this.  ts->doff[0..nd] holds the side's document offsets, ts->dpos[] the next token
+// position of every row.  Tokens at positions < limit are delivered to rowbufs (FIXED) / ts->dout (RAGGED).
+template <int MODE>
+__device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ bytes, TileSmem* ts, int nd,
+                                          int lane, int32_t limit, int32_t* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok) {
+    const int64_t S = ts->doff[0], E = ts->doff[nd];
+    if (E <= S) return;
+    const int64_t base = S & ~(int64_t)15;
+    const int32_t n_win = (int32_t)((E - base + 16 * WIN_LANES - 1) / (16 * WIN_LANES));
+    uint32_t carry = 1u << 15;    // the byte before the tile is whitespace, nothing spills in
+    for (int32_t w = 0; w < n_win; ++w) {
+        const int64_t wbase = base + (int64_t)w * (16 * WIN_LANES);
+        const int64_t a = wbase + lane * 16;
+        // document starts inside this window -> bits per piece
+        ts->bnd[lane] = 0;
+        __syncwarp();
+        if (lane + 1 < nd) {
+            const int64_t o = ts->doff[lane + 1] - wbase;
+            if (o >= 0 && o < 16 * 32) atomicOr(&ts->bnd[o >> 4], 1u << (o & 15));
+        }
+        __syncwarp();
+        uint32_t ws18 = 0xFFFFu;
+        if (a < E) {
+            const uint4 v = ldg128(bytes + a);
+            ws18 = classify16(v, bytes, a, S, E, ts->doff, nd);
+        }
+        uint32_t prev = __shfl_up_sync(FULL_MASK, ws18, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(FULL_MASK, ws18, WIN_LANES - 1);
+        const uint32_t nw = ~(ws18 | (prev >> 16)) & 0xFFFFu;
+        uint32_t st = nw & (~((nw << 1) | ((~prev >> 15) & 1u)) | ts->bnd[lane]);
+        if (lane >= WIN_LANES) st = 0;                      // look-ahead pieces: their words belong to the next window
+        // non-whitespace bits of the following pieces: word ends without touching memory
+        uint64_t win = nw;
+        {
+            const uint32_t n1 = __shfl_down_sync(FULL_MASK, nw, 1), n2 = __shfl_down_sync(FULL_MASK, nw, 2), n3 = __shfl_down_sync(FULL_MASK, nw, 3);
+            if (lane + 1 < 32) win |= (uint64_t)n1 << 16;
+            if (lane + 2 < 32) win |= (uint64_t)n2 << 32;
+            if (lane + 3 < 32) win |= (uint64_t)n3 << 48;
+        }
+        const int known = 16 * ((32 - lane) < 4 ? (32 - lane) : 4);
+        // ---- compact my word starts into the word list
+        const int cnt = __popc(st);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        int k = incl - cnt;
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            const uint64_t z = (~win) >> (b + 1);
+            int run = z ? __ffsll((long long)z) : 65;       // bytes from the word start to the first whitespace
+            if (b + run >= known) run = 0;                  // not decided inside the window registers
+            ts->wlist[k++] = (uint16_t)((lane * 16 + b) | (run << 9));
+        }
+        __syncwarp();
+        // ---- one word per lane
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < total;
+            int doc = 0x7FFF;
+            uint32_t nt = 0, val = 0;
+            bool pending = false;
+            int64_t p = 0;
+            if (has) {
+                p = wbase + (ts->wlist[j] & 511u);
+                doc = doc_of(ts->doff, nd, p);
             }
-            const int32_t total = __shfl_sync(FULL_MASK, incl, G - 1, G);
-            if (MODE != MODE_COUNT) {
-                int32_t q = pos + incl - cnt;
-                for (int j = 0; j < nwords; j++) {
-                    const uint32_t enc = scratch[j * 32 + lane];
-                    if (enc & 0x80000000u) {
-                        const int32_t t = (int32_t)(enc & 0x7FFFFFFFu);
-                        if (t == T.eos || t == T.bos) flags |= 2u;
-                        if (MODE == MODE_FIXED) { if (q < limit) rowbuf[q] = t; }
-                        else if (q < glimit) gout[q] = t;
-                        q++;
-                    } else {
-                        const Slot* sl = &C.slots[enc];
-                        const uint32_t nt = sl->ntok;
-                        const uint32_t t0 = sl->t0, t1 = sl->t1;
-                        for (uint32_t k = 0; k < nt; k++) {
-                            const int32_t t = (int32_t)(nt <= 2 ? (k == 0 ? t0 : t1) : C.tok_arena[t0 + k]);
-                            if (t == T.eos || t == T.bos) flags |= 2u;
-                            if (MODE == MODE_FIXED) { if (q < limit) rowbuf[q] = t; }
-                            else if (q < glimit) gout[q] = t;
-                            q++;
-                        }
+            // a word of a row that is already full cannot matter (and need not be known): skip its lookup
+            if (has && ts->dpos[doc] < limit) {
+                const int run = (int)(ts->wlist[j] >> 9);
+                const int64_t e_doc = ts->doff[doc + 1];
+                int64_t end = run ? p + run : slow_word_end(bytes, p + 1, e_doc);
+                if (end > e_doc) end = e_doc;
+                if (end < e_doc && bytes[end] == 0x0A) end++;          // \S+\n?  (tokenize.py:106)
+                const uint32_t len = (uint32_t)(end - p);
+                uint64_t k0, k1, k2; uint32_t h;
+                if (len <= KEY_INLINE) { load_key24(bytes, p, len, &k0, &k1, &k2); h = hash_key24(k0, k1, k2, len); }
+                else { k1 = hash_long(bytes + p, len); k0 = 0; k2 = 0; h = fmix32((uint32_t)k1 ^ (uint32_t)(k1 >> 32)); }
+                val = cache_find_or_insert(C, bytes + p, len, k0, k1, k2, h, insert_ok);
+                const uint32_t kind = val & VAL_KIND;
+                if (kind == VAL_SINGLE) nt = 1;
+                else if (kind == VAL_MULTI) nt = C.tok_arena[val & VAL_PAYLOAD];
+                else pending = true;                                   // BPE not run yet (counts as 0 tokens for now)
+            }
+            // position of my first token: segmented inclusive scan of nt over equal doc
+            uint32_t sc = nt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o);
+                const int dsrc = __shfl_up_sync(FULL_MASK, doc, o);
+                if (lane >= o && dsrc == doc) sc += t;
+            }
+            const int dnext = __shfl_down_sync(FULL_MASK, doc, 1);
+            int32_t q = 0;
+            if (has) q = ts->dpos[doc] + (int32_t)(sc - nt);
+            // q is a lower bound of the word's position while earlier words are pending: if even that is past the
+            // row's end the word is irrelevant, otherwise the row must be redone after k_bpe_pending
+            if (pending && q < limit) atomicOr(&ts->dflag[doc], F_DIRTY);
+            __syncwarp();
+            if (has && (lane == 31 || dnext != doc)) ts->dpos[doc] = q + (int32_t)nt;
+            if (MODE != MODE_COUNT && has && nt) {
+                int32_t* dst; int32_t lim;
+                if (MODE == MODE_FIXED) { dst = rowbufs + (size_t)doc * Wp; lim = limit; }
+                else { dst = ids_out + ts->dout[doc]; lim = ts->dkeep[doc]; }
+                uint32_t fl = 0;
+                if (nt == 1) {
+                    const int32_t t = (int32_t)(val & VAL_PAYLOAD);
+                    if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
+                    if (t == T.pad) fl |= F_PADTOK;
+                    if (q < lim) dst[q] = t;
+                } else {
+                    const uint32_t* src = C.tok_arena + (val & VAL_PAYLOAD) + 1;
+                    for (uint32_t i = 0; i < nt && q < lim; i++, q++) {
+                        const int32_t t = (int32_t)src[i];
+                        if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
+                        if (t == T.pad) fl |= F_PADTOK;
+                        dst[q] = t;
                     }
                 }
+                if (fl) atomicOr(&ts->dflag[doc], fl);
             }
-            pos += total;
+            __syncwarp();
+        }
+        if (MODE == MODE_FIXED) {                            // every row of the tile already full: stop reading
+            const int32_t pmin = __reduce_min_sync(FULL_MASK, lane < nd ? ts->dpos[lane] : 0x7FFFFFFF);
+            if (pmin >= limit) break;
         }
     }
-};
+    __syncwarp();
+}
 
-template <int G, int MODE>
-__global__ void __launch_bounds__(256) k_rows(DevTables T, WordCache C, RowArgs A) {
-    using K = RowKernel<G, MODE>;
-    constexpr int D = K::D;
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) k_rows(DevTables T, WordCache C, RowArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int gl = lane % G, g = lane / G;
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wib * K::MAXW * 32;
-    int32_t* rowbufs = reinterpret_cast<int32_t*>(smem_raw + (size_t)wpb * K::MAXW * 32 * 4);
-    const int32_t W = A.W;
+    const int32_t W = A.W, D = A.D;
     const int32_t Wp = (W + 3) & ~3;
-    int32_t* rowbuf = MODE == MODE_FIXED ? rowbufs + ((size_t)wib * D + g) * Wp : nullptr;
+    const size_t per_warp = sizeof(TileSmem) + (MODE == MODE_FIXED ? (size_t)D * Wp * 4 : 0);
+    TileSmem* ts = reinterpret_cast<TileSmem*>(smem_raw + (size_t)wib * per_warp);
+    int32_t* rowbufs = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ts) + sizeof(TileSmem));
 
     const unsigned long long n_items = A.row_list ? C.ctr[C_REDO] : (unsigned long long)A.n_rows;
-    const unsigned long long n_tiles = (n_items + D - 1) / D;
+    // a row list holds arbitrary rows: they are not contiguous in the text, so its tiles hold one document
+    const unsigned long long Dt = A.row_list ? 1ull : (unsigned long long)D;
+    const unsigned long long n_tiles = (n_items + Dt - 1) / Dt;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * wpb;
-    unsigned long long tok_total = 0;
+    const int32_t limit = MODE == MODE_FIXED ? W - 1 : 0x7FFFFFFF;
+    const bool insert_ok = !A.row_list && MODE != MODE_RAGGED;   // second passes only look words up
+    uint32_t tok_total = 0;
     for (unsigned long long tile = (unsigned long long)blockIdx.x * wpb + wib; tile < n_tiles; tile += n_warps) {
-        const unsigned long long item = tile * D + g;
-        const bool active = item < n_items;
-        const int64_t r = active ? (A.row_list ? (int64_t)A.row_list[item] : (int64_t)item) : 0;
-        int64_t sa = 0, ea = 0, sb = 0, eb = 0;
-        if (active) {
-            sa = A.a.off[r]; ea = A.a.off[r + 1];
-            if (A.has_pair) { sb = A.b.off[r]; eb = A.b.off[r + 1]; }
+        const int64_t r0 = A.row_list ? (int64_t)A.row_list[tile] : (int64_t)(tile * Dt);
+        const unsigned long long left = n_items - tile * Dt;
+        const int nd = (int)(Dt < left ? Dt : left);
+        // ---- set up the tile
+        if (lane < nd) ts->doff[lane] = A.a.off[r0 + lane];
+        if (lane == 0) ts->doff[nd] = A.a.off[r0 + nd];            // nd may be 32: 33 offsets
+        if (lane < nd) {
+            ts->dpos[lane] = 1;                                    // position 0 is <s> (tokenize.py:135)
+            ts->dflag[lane] = 0;
+            if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = T.bos; }
+            if (MODE == MODE_RAGGED) {
+                const int64_t ro = A.row_off[r0 + lane];
+                const int32_t kp = A.keep[r0 + lane];
+                ts->dout[lane] = ro; ts->dkeep[lane] = kp;
+                if (kp > 0) A.ids[ro] = T.bos;
+            }
         }
-        // where the row's tokens go
-        int32_t limit, glimit = 0; int32_t* gout = nullptr;
-        if (MODE == MODE_FIXED) limit = W - 1;
-        else if (MODE == MODE_COUNT) limit = 0x7FFFFFFF;
-        else { limit = 0x7FFFFFFF; if (active) { gout = A.ids + A.row_off[r]; glimit = A.keep[r]; } }
-
-        uint32_t flags = 0;
-        int32_t pos = 1;                                           // position 0 is <s> (tokenize.py:135)
-        if (MODE == MODE_FIXED) { if (gl == 0 && active && limit > 0) rowbuf[0] = T.bos; }
-        else if (MODE == MODE_RAGGED) { if (gl == 0 && active && glimit > 0) gout[0] = T.bos; }
         __syncwarp();
-        K::scan_side(T, C, A.a, sa, ea, active, gl, scratch, lane, pos, limit, flags, rowbuf, gout, glimit);
-        const int32_t nA = pos - 1;
+        walk_side<MODE>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok);
         if (A.has_pair) {
             // ... </s> </s> B   (tokenize.py:237-239)
-            if (gl == 0 && active) {
-                if (MODE == MODE_FIXED) { if (pos < limit) rowbuf[pos] = T.eos; if (pos + 1 < limit) rowbuf[pos + 1] = T.eos; }
-                else if (MODE == MODE_RAGGED) { if (pos < glimit) gout[pos] = T.eos; if (pos + 1 < glimit) gout[pos + 1] = T.eos; }
+            if (lane < nd) {
+                const int32_t pos = ts->dpos[lane];
+                ts->dnA[lane] = pos - 1;
+                if (MODE == MODE_FIXED) { int32_t* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = T.eos; if (pos + 1 < limit) rb[pos + 1] = T.eos; }
+                if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->dout[lane]; const int32_t kp = ts->dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
+                ts->dpos[lane] = pos + 2;
             }
-            pos += 2;
-            K::scan_side(T, C, A.b, sb, eb, active, gl, scratch, lane, pos, limit, flags, rowbuf, gout, glimit);
+            __syncwarp();
+            if (lane < nd) ts->doff[lane] = A.b.off[r0 + lane];
+            if (lane == 0) ts->doff[nd] = A.b.off[r0 + nd];
+            __syncwarp();
+            walk_side<MODE>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok);
         }
-        if (gl == 0 && active) {                                   // closing </s>
-            if (MODE == MODE_FIXED) { if (pos < limit) rowbuf[pos] = T.eos; }
-            else if (MODE == MODE_RAGGED) { if (pos < glimit) gout[pos] = T.eos; }
-        }
-        const int32_t L = pos + 1;                                 // framed length (>= W when the walk stopped early)
-        // merge per-lane flags over the group
-#pragma unroll
-        for (int o = 1; o < G; o <<= 1) flags |= __shfl_xor_sync(FULL_MASK, flags, o, G);
-        const bool dirty = flags & 1u;
-        if (active && gl == 0 && dirty) {
-            if (!A.row_list) {
-                unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL);
-                A.redo_list[k] = (uint32_t)r;
-            } else {
-                atomicAdd(&C.ctr[C_ERR], 1ULL);   // cannot happen: every word of a redo row was inserted in pass 1
+        // ---- closing </s>, row bookkeeping (one lane per row)
+        if (lane < nd) {
+            const int32_t pos = ts->dpos[lane];
+            const int32_t dL = pos + 1;                                // framed length (>= W when the walk stopped early)
+            if (MODE == MODE_FIXED) { if (pos < limit) rowbufs[(size_t)lane * Wp + pos] = T.eos; }
+            if (MODE == MODE_RAGGED) { if (pos < ts->dkeep[lane]) A.ids[ts->dout[lane] + pos] = T.eos; }
+            const uint32_t fl = ts->dflag[lane];
+            if (fl & F_DIRTY) {
+                if (!A.row_list) { const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL); A.redo_list[k] = (uint32_t)(r0 + lane); }
+                else atomicAdd(&C.ctr[C_ERR], 1ULL);   // cannot happen: every word of a redo row was inserted in pass 1
+            } else if (MODE == MODE_FIXED) {
+                const int64_t dr = r0 + lane;
+                const int32_t Lr = dL < W ? dL : W;
+                if (A.row_len) A.row_len[dr] = Lr;
+                if (!(fl & F_PADTOK)) tok_total += (uint32_t)Lr;       // rows with a pad id inside are counted from their mask
+                if (A.has_pair) {
+                    const SeqDesc sd = seq_describe(ts->dnA[lane], dL, W);
+                    ts->dsd[lane] = sd;
+                    if (A.seq_len) A.seq_len[dr] = sd.m;
+                    if (A.status) A.status[dr] = (uint8_t)sd.err;
+                    if ((fl & F_SPECIAL) || !T.specials_distinct) { const unsigned long long k = atomicAdd(&C.ctr[C_FIX], 1ULL); A.fix_list[k] = (uint32_t)dr; }
+                }
             }
+            if (MODE == MODE_COUNT) A.L[r0 + lane] = dL;
         }
-        if (MODE == MODE_COUNT) {
-            if (active && gl == 0) A.L[r] = L;
-            continue;
-        }
-        if (MODE == MODE_RAGGED) continue;
         __syncwarp();
-        // ---- FIXED: the warp writes its D rows --------------------------------------------------------
-        const bool need_fix = A.has_pair && ((flags & 2u) || !T.specials_distinct);
-        for (int d = 0; d < D; d++) {
-            const int src = d * G;
-            const bool d_active = __shfl_sync(FULL_MASK, (int)active, src);
-            const bool d_dirty = __shfl_sync(FULL_MASK, (int)dirty, src);
-            if (!d_active || d_dirty) continue;
-            const int64_t dr = __shfl_sync(FULL_MASK, (long long)r, src);
-            const int32_t dL = __shfl_sync(FULL_MASK, L, src);
-            const int32_t dnA = __shfl_sync(FULL_MASK, nA, src);
-            const bool d_fix = __shfl_sync(FULL_MASK, (int)need_fix, src);
+        if (MODE != MODE_FIXED) continue;
+        // ---- FIXED: the warp writes its rows -----------------------------------------------------------
+        for (int d = 0; d < nd; d++) {
+            const uint32_t fl = ts->dflag[d];
+            if (fl & F_DIRTY) continue;
+            const int64_t dr = r0 + d;
+            const int32_t dL = ts->dpos[d] + 1;
             const int32_t Lr = dL < W ? dL : W;
             const bool trunc = dL >= W;
-            const int32_t* rb = rowbufs + ((size_t)wib * D + d) * Wp;
-            SeqDesc sd;
-            if (A.has_pair) sd = seq_describe(dnA, dL, W);
-            int32_t ntok_row = 0;
+            const bool generic_mask = (fl & F_PADTOK) != 0;
+            const int32_t* rb = rowbufs + (size_t)d * Wp;
             if ((W & 15) == 0) {
                 for (int32_t i0 = lane * 4; i0 < W; i0 += 128) {
                     int4 v = *reinterpret_cast<const int4*>(rb + i0);
-                    int32_t x[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t mk = 0, ttw = 0, sqw = 0;
+                    uint32_t mk;
+                    if (i0 + 4 <= Lr && !(trunc && i0 + 4 == W) && !generic_mask) {
+                        mk = 0x01010101u;                               // four real tokens
+                    } else if (i0 >= Lr && !generic_mask) {
+                        v = make_int4(T.pad, T.pad, T.pad, T.pad); mk = 0;
+                    } else {
+                        int32_t x[4] = {v.x, v.y, v.z, v.w};
+                        mk = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int32_t i = i0 + k;
-                        int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : x[k]) : T.pad;
-                        x[k] = t;
-                        const uint32_t on = t != T.pad;
-                        mk |= on << (8 * k);
-                        ntok_row += (int32_t)on;
-                        if (A.has_pair) {
-                            int32_t sv = i < sd.m ? seq_value(sd, i) : 0;
-                            int32_t tv = (sd.m == W && i == W - 1) ? (int32_t)A.eos_i8 : sv;
-                            ttw |= ((uint32_t)tv & 0xFFu) << (8 * k);
-                            sqw |= ((uint32_t)(i < sd.m ? sv : -2) & 0xFFu) << (8 * k);
+                        for (int k = 0; k < 4; k++) {
+                            const int32_t i = i0 + k;
+                            x[k] = i < Lr ? ((trunc && i == W - 1) ? T.eos : x[k]) : T.pad;
+                            mk |= (uint32_t)(x[k] != T.pad) << (8 * k);
                         }
+                        v = make_int4(x[0], x[1], x[2], x[3]);
+                        if (generic_mask) tok_total += (uint32_t)__popc(mk);
                     }
-                    st_cs128(A.ids + dr * W + i0, make_uint4((uint32_t)x[0], (uint32_t)x[1], (uint32_t)x[2], (uint32_t)x[3]));
+                    st_cs128(A.ids + dr * W + i0, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
                     if (A.mask) st_cs32(A.mask + dr * W + i0, mk);
-                    if (A.has_pair && A.tt) st_cs32(A.tt + dr * W + i0, ttw);
-                    if (A.has_pair && A.seq) st_cs32(A.seq + dr * W + i0, sqw);
+                    if (A.has_pair && (A.tt || A.seq)) {
+                        uint32_t ttw, sqw;
+                        seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                        if (A.tt) st_cs32(A.tt + dr * W + i0, ttw);
+                        if (A.seq) st_cs32(A.seq + dr * W + i0, sqw);
+                    }
                 }
             } else {
                 for (int32_t i = lane; i < W; i += 32) {
-                    int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : rb[i]) : T.pad;
+                    const int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : rb[i]) : T.pad;
                     A.ids[dr * W + i] = t;
-                    const uint32_t on = t != T.pad;
-                    ntok_row += (int32_t)on;
-                    if (A.mask) A.mask[dr * W + i] = (uint8_t)on;
+                    if (generic_mask) tok_total += (uint32_t)(t != T.pad);
+                    if (A.mask) A.mask[dr * W + i] = (uint8_t)(t != T.pad);
                     if (A.has_pair) {
-                        int32_t sv = i < sd.m ? seq_value(sd, i) : 0;
-                        int32_t tv = (sd.m == W && i == W - 1) ? (int32_t)A.eos_i8 : sv;
+                        const SeqDesc& sd = ts->dsd[d];
+                        const int32_t sv = i < sd.m ? seq_value(sd, i) : 0;
+                        const int32_t tv = (sd.m == W && i == W - 1) ? (int32_t)A.eos_i8 : sv;
                         if (A.tt) A.tt[dr * W + i] = (int8_t)tv;
                         if (A.seq) A.seq[dr * W + i] = (int8_t)(i < sd.m ? sv : -2);
                     }
                 }
             }
-            ntok_row = __reduce_add_sync(FULL_MASK, ntok_row);
-            if (lane == 0) {
-                if (A.row_len) A.row_len[dr] = Lr;
-                if (A.has_pair) {
-                    if (A.seq_len) A.seq_len[dr] = sd.m;
-                    if (A.status) A.status[dr] = (uint8_t)sd.err;
-                    if (d_fix) { unsigned long long k = atomicAdd(&C.ctr[C_FIX], 1ULL); A.fix_list[k] = (uint32_t)dr; }
-                }
-                tok_total += (unsigned long long)ntok_row;
-            }
         }
         __syncwarp();
     }
-    if (MODE == MODE_FIXED && lane == 0 && tok_total) atomicAdd(&C.ctr[C_TOKENS], tok_total);
+    if (MODE == MODE_FIXED) {
+        tok_total = __reduce_add_sync(FULL_MASK, tok_total);   // < 2^32 per warp
+        if (lane == 0 && tok_total) atomicAdd(&C.ctr[C_TOKENS], (unsigned long long)tok_total);
+    }
 }
 
 }  // namespace gzt

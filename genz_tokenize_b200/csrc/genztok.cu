@@ -191,7 +191,7 @@ int ensure_cache(genztok_t* h, DeviceCtx* d) {
     const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
     CU(d->slots.ensure(slots * sizeof(Slot)));
     CU(d->key_arena.ensure(B + 64));
-    CU(d->tok_arena.ensure((B + 64) * 4));
+    CU(d->tok_arena.ensure((2 * B + 64) * 4));
     CU(d->pending.ensure((B / 2 + 64) * 4));
     CU(d->ctr.ensure(C_COUNT * 8));
     CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), d->stream));
@@ -199,37 +199,44 @@ int ensure_cache(genztok_t* h, DeviceCtx* d) {
     WordCache& C = d->C;
     C.slots = d->slots.as<Slot>(); C.mask = (uint32_t)(slots - 1);
     C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + 64;
-    C.tok_arena = d->tok_arena.as<uint32_t>(); C.tok_cap = B + 64;
+    C.tok_arena = d->tok_arena.as<uint32_t>(); C.tok_cap = 2 * B + 64;
     C.pending = d->pending.as<uint32_t>(); C.pending_cap = B / 2 + 64;
     C.ctr = d->ctr.as<unsigned long long>();
     d->cache_ready = true;
     return GENZTOK_OK;
 }
 
-int pick_group(genztok_t* h, int64_t bytes_a, int64_t bytes_b, int64_t n) {
-    if (h->force_group) return (int)h->force_group;
-    int64_t avg = n > 0 ? std::max(bytes_a, bytes_b) / n : 0;
-    if (avg <= 36) return 2;
-    if (avg <= 100) return 4;
-    if (avg <= 230) return 8;
-    if (avg <= 500) return 16;
-    return 32;
+// Documents per warp tile: aim at ~26 sixteen-byte pieces of text per window, bounded by the shared memory
+// the staged rows need (MODE_FIXED) so that at least two 8-warp blocks fit an SM.
+int pick_tile_docs(genztok_t* h, const DeviceCtx* d, int64_t bytes_a, int64_t bytes_b, int64_t n, int32_t W, bool fixed) {
+    int D;
+    if (h->force_group) D = (int)h->force_group;
+    else {
+        const int64_t avg = n > 0 ? std::max<int64_t>(std::max(bytes_a, bytes_b) / n, 1) : 1;
+        D = (int)std::min<int64_t>(32, std::max<int64_t>(1, 416 / avg));
+    }
+    if (fixed) {
+        const size_t row = (((size_t)W + 3) & ~(size_t)3) * 4;
+        while (D > 1 && 8 * (sizeof(TileSmem) + (size_t)D * row) > d->smem_optin / 2) D--;
+    }
+    return D;
 }
 
-template <int G, int MODE>
-int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
-    constexpr int D = 32 / G;
+template <int MODE>
+int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
+    const int D = A.row_list ? 1 : A.D;
+    const size_t row = (((size_t)A.W + 3) & ~(size_t)3) * 4;
+    auto smem_for = [&](int w) { return (size_t)w * (sizeof(TileSmem) + (MODE == MODE_FIXED ? (size_t)A.D * row : 0)); };
     int wpb = 8;
-    auto smem_for = [&](int w) { return (size_t)w * 8 * 32 * 4 + (MODE == MODE_FIXED ? (size_t)w * D * (((size_t)A.W + 3) & ~(size_t)3) * 4 : 0); };
     while (wpb > 1 && smem_for(wpb) > d->smem_optin) wpb >>= 1;
     const size_t smem = smem_for(wpb);
     if (smem > d->smem_optin) return fail(h, GENZTOK_E_LIMIT, "row of %d ids does not fit shared memory", A.W);
-    auto kern = k_rows<G, MODE>;
+    auto kern = k_rows<MODE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
     if (occ < 1) occ = 1;
-    int64_t tiles = (n_items_hint + D - 1) / D;
+    const int64_t tiles = (n_items_hint + D - 1) / D;
     int64_t blocks = std::min<int64_t>((tiles + wpb - 1) / wpb, (int64_t)d->sm_count * occ);
     if (blocks < 1) blocks = 1;
     LaunchScope ls(h, d, name);
@@ -238,29 +245,13 @@ int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st,
     return GENZTOK_OK;
 }
 
-template <int MODE>
-int launch_rows(genztok_t* h, DeviceCtx* d, int G, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_hint) {
-    switch (G) {
-        case 2: return launch_rows_t<2, MODE>(h, d, A, st, name, n_hint);
-        case 4: return launch_rows_t<4, MODE>(h, d, A, st, name, n_hint);
-        case 8: return launch_rows_t<8, MODE>(h, d, A, st, name, n_hint);
-        case 16: return launch_rows_t<16, MODE>(h, d, A, st, name, n_hint);
-        default: return launch_rows_t<32, MODE>(h, d, A, st, name, n_hint);
-    }
-}
-
-// Can the fixed-layout kernel stage rows of W ids?  (G = 32, one warp per block is the smallest footprint)
-bool fixed_fits(const DeviceCtx* d, int32_t W) { return (size_t)8 * 32 * 4 + (((size_t)W + 3) & ~(size_t)3) * 4 <= d->smem_optin; }
-int clamp_group_for_smem(const DeviceCtx* d, int G, int32_t W) {
-    // prefer >= 4 warps per block: raise G (fewer rows per warp) until the tile fits
-    while (G < 32 && (size_t)4 * 8 * 32 * 4 + (size_t)4 * (32 / G) * (((size_t)W + 3) & ~(size_t)3) * 4 > d->smem_optin) G <<= 1;
-    return G;
-}
+// Can the fixed-layout kernel stage one row of W ids (one document per tile, one warp per block)?
+bool fixed_fits(const DeviceCtx* d, int32_t W) { return sizeof(TileSmem) + (((size_t)W + 3) & ~(size_t)3) * 4 <= d->smem_optin; }
 
 int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
-        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)chunk_bytes, force);
+        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
@@ -303,14 +294,14 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     A.row_len = P.row_len; A.seq_len = P.seq_len; A.status = P.row_status;
     A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>();
     A.eos_i8 = eos_as_i8(d);
-    int G = clamp_group_for_smem(d, pick_group(h, a.nbytes, b ? b->nbytes : 0, n), W);
-    rc = launch_rows<MODE_FIXED>(h, d, G, A, st, "k_rows_fixed", n);
+    A.D = pick_tile_docs(h, d, a.nbytes, b ? b->nbytes : 0, n, W, true);
+    rc = launch_rows<MODE_FIXED>(h, d, A, st, "k_rows_fixed", n);
     if (rc) return rc;
     rc = launch_bpe(h, d, st);
     if (rc) return rc;
     RowArgs R = A;
     R.row_list = d->redo.as<uint32_t>();
-    rc = launch_rows<MODE_FIXED>(h, d, G, R, st, "k_rows_fixed_redo", std::min<int64_t>(n, (int64_t)d->sm_count * 64));
+    rc = launch_rows<MODE_FIXED>(h, d, R, st, "k_rows_fixed_redo", std::min<int64_t>(n, (int64_t)d->sm_count * 64));
     if (rc) return rc;
     if (b && (A.tt || A.seq || A.status || A.seq_len)) {
         PostArgs Q{};
@@ -456,13 +447,13 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     std::string n = name ? name : "";
     if (n == "max_chunk_bytes") {
         for (DeviceCtx* d : h->devs) if (d->cache_ready) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes must be set before the first encode");
-        if (value < 4096) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes too small");
+        if (value < 4096 || value > (1ll << 29)) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes must be in [4 KiB, 512 MiB]");
         h->max_chunk_bytes = value;
     } else if (n == "chunk_rows") {
         if (value < 1) return fail(h, GENZTOK_E_INVALID, "chunk_rows < 1");
         h->chunk_rows = value;
     } else if (n == "group") {
-        if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32) return fail(h, GENZTOK_E_INVALID, "group must be 0,2,4,8,16,32");
+        if (value < 0 || value > 32) return fail(h, GENZTOK_E_INVALID, "group (documents per warp tile) must be 0 (auto) or 1..32");
         h->force_group = value;
     } else return fail(h, GENZTOK_E_INVALID, "unknown option %s", n.c_str());
     return GENZTOK_OK;
@@ -681,11 +672,11 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         RowArgs A{};
         A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = flags;
         A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8;
-        const int G = pick_group(h, tb, pb, m);
-        FAIL_RC(launch_rows<MODE_COUNT>(h, d, G, A, st, "k_rows_count", m));
+        A.D = pick_tile_docs(h, d, tb, pb, m, 0, false);
+        FAIL_RC(launch_rows<MODE_COUNT>(h, d, A, st, "k_rows_count", m));
         FAIL_RC(launch_bpe(h, d, st));
         RowArgs R = A; R.row_list = d->redo.as<uint32_t>();
-        FAIL_RC(launch_rows<MODE_COUNT>(h, d, G, R, st, "k_rows_count_redo", std::min<int64_t>(m, (int64_t)d->sm_count * 64)));
+        FAIL_RC(launch_rows<MODE_COUNT>(h, d, R, st, "k_rows_count_redo", std::min<int64_t>(m, (int64_t)d->sm_count * 64)));
         LenArgs LA{d->L.as<int32_t>(), m, (int32_t)has_max_len, has_max_len ? max_len : 0, padding ? 1 : 0, truncation ? 1 : 0,
                    d->keep.as<int32_t>(), d->out_len.as<int64_t>(), d->tail.as<uint8_t>()};
         { LaunchScope ls(h, d, "k_row_lens"); k_row_lens<<<(unsigned)std::min<int64_t>((m + 255) / 256, 4096), 256, 0, st>>>(LA); }
@@ -698,7 +689,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         { LaunchScope ls(h, d, "k_reset_lists"); k_reset_lists<<<1, 1, 0, st>>>(d->C); }
         RowArgs E = A;
         E.ids = d->ids.as<int32_t>(); E.row_off = d->row_off.as<int64_t>(); E.keep = d->keep.as<int32_t>();
-        FAIL_RC(launch_rows<MODE_RAGGED>(h, d, G, E, st, "k_rows_ragged", m));
+        FAIL_RC(launch_rows<MODE_RAGGED>(h, d, E, st, "k_rows_ragged", m));
         PostArgs Q{};
         Q.ids = d->ids.as<int32_t>(); Q.row_off = d->row_off.as<int64_t>(); Q.n_rows = m; Q.keep = d->keep.as<int32_t>(); Q.tail = d->tail.as<uint8_t>();
         Q.mask = d->mask.as<uint8_t>(); Q.has_pair = has_pair; Q.row_len = d->row_len.as<int32_t>();

@@ -155,9 +155,9 @@ def test_synthetic_vs_oracle(tok, oracle, cfg):
     assert_matches_oracle(be, orc, what=str(cfg))
 
 
-@pytest.mark.parametrize("group", [2, 4, 8, 16, 32])
-def test_every_group_width_and_small_chunks(oracle, group):
-    # force each lanes-per-document variant of the row kernel, tiny chunks (many launches, cache resets)
+@pytest.mark.parametrize("group", [1, 2, 3, 8, 17, 32])
+def test_every_tile_size_and_small_chunks(oracle, group):
+    # force the number of documents per warp tile, tiny chunks (many launches, cache resets)
     from genz_tokenize_b200 import Tokenize, workload
     tok = Tokenize()
     tok.set_option("max_chunk_bytes", 1 << 15)
