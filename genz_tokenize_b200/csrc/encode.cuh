@@ -69,7 +69,7 @@ struct __align__(16) TileSmem {
     int32_t dkeep[32];         // RAGGED: tokens to keep
     uint32_t bnd[32];          // document-start bits per piece of the current window
     SeqDesc dsd[32];           // FIXED pairs: token-type description per row
-    uint16_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown)
+    uint32_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown) | document << 16
 };
 
 // ---- byte classification -----------------------------------------------------------------------
@@ -302,6 +302,10 @@ template <int MODE>
 __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ bytes, TileSmem* ts, int nd,
                                           int lane, int32_t limit, int32_t* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok) {
     const int64_t S = ts->doff[0], E = ts->doff[nd];
+    // documents that are empty share their start with the next one: then the per-piece start bits cannot number
+    // documents and every word finds its document by binary search instead
+    const bool has_empty = __any_sync(FULL_MASK, lane < nd && ts->doff[lane + 1] == ts->doff[lane]);
+    int dbase = 0;                // documents that started before the current window
     if (E <= S) return;
     const int64_t base = S & ~(int64_t)15;
     const int32_t n_win = (int32_t)((E - base + 16 * WIN_LANES - 1) / (16 * WIN_LANES));
@@ -337,20 +341,24 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             if (lane + 3 < 32) win |= (uint64_t)n3 << 48;
         }
         const int known = 16 * ((32 - lane) < 4 ? (32 - lane) : 4);
-        // ---- compact my word starts into the word list
+        // ---- compact my word starts into the word list (and number the documents by counting start bits)
+        const uint32_t b16 = ts->bnd[lane];
         const int cnt = __popc(st);
-        int incl = cnt;
+        int incl = cnt | (__popc(b16) << 16);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(FULL_MASK, incl, 31);
-        int k = incl - cnt;
+        const int total = __shfl_sync(FULL_MASK, incl, 31) & 0xFFFF;
+        const int dlane = dbase + (incl >> 16) - __popc(b16);           // document of the byte before my piece
+        dbase += __shfl_sync(FULL_MASK, incl, WIN_LANES - 1) >> 16;
+        int k = (incl & 0xFFFF) - cnt;
         while (st) {
             const int b = __ffs(st) - 1;
             st &= st - 1;
             const uint64_t z = (~win) >> (b + 1);
             int run = z ? __ffsll((long long)z) : 65;       // bytes from the word start to the first whitespace
             if (b + run >= known) run = 0;                  // not decided inside the window registers
-            ts->wlist[k++] = (uint16_t)((lane * 16 + b) | (run << 9));
+            const int doc = dlane + __popc(b16 & ((2u << b) - 1));
+            ts->wlist[k++] = (uint32_t)((lane * 16 + b) | (run << 9) | (doc << 16));
         }
         __syncwarp();
         // ---- one word per lane
@@ -361,13 +369,15 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             uint32_t nt = 0, val = 0;
             bool pending = false;
             int64_t p = 0;
+            uint32_t wl = 0;
             if (has) {
-                p = wbase + (ts->wlist[j] & 511u);
-                doc = doc_of(ts->doff, nd, p);
+                wl = ts->wlist[j];
+                p = wbase + (wl & 511u);
+                doc = has_empty ? doc_of(ts->doff, nd, p) : (int)(wl >> 16);
             }
             // a word of a row that is already full cannot matter (and need not be known): skip its lookup
             if (has && ts->dpos[doc] < limit) {
-                const int run = (int)(ts->wlist[j] >> 9);
+                const int run = (int)((wl >> 9) & 127u);
                 const int64_t e_doc = ts->doff[doc + 1];
                 int64_t end = run ? p + run : slow_word_end(bytes, p + 1, e_doc);
                 if (end > e_doc) end = e_doc;
@@ -430,7 +440,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) k_rows(DevTables T, WordCache C, RowArgs A) {
+__global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D;
@@ -523,11 +533,12 @@ __global__ void __launch_bounds__(256, 3) k_rows(DevTables T, WordCache C, RowAr
                 for (int32_t i0 = lane * 4; i0 < W; i0 += 128) {
                     int4 v = *reinterpret_cast<const int4*>(rb + i0);
                     uint32_t mk;
-                    if (i0 + 4 <= Lr && !(trunc && i0 + 4 == W) && !generic_mask) {
-                        mk = 0x01010101u;                               // four real tokens
-                    } else if (i0 >= Lr && !generic_mask) {
-                        v = make_int4(T.pad, T.pad, T.pad, T.pad); mk = 0;
-                    } else {
+                    if (!generic_mask) {
+                        const int32_t c = Lr - i0;                      // real tokens in this quad: branch-free select
+                        v.x = c > 0 ? v.x : T.pad; v.y = c > 1 ? v.y : T.pad; v.z = c > 2 ? v.z : T.pad; v.w = c > 3 ? v.w : T.pad;
+                        if (trunc && i0 + 4 == W) v.w = T.eos;
+                        mk = c >= 4 ? 0x01010101u : (c <= 0 ? 0u : (0x01010101u & ((1u << (8 * c)) - 1)));
+                    } else {                                            // a pad id inside the text: mask by value
                         int32_t x[4] = {v.x, v.y, v.z, v.w};
                         mk = 0;
 #pragma unroll
@@ -537,7 +548,7 @@ __global__ void __launch_bounds__(256, 3) k_rows(DevTables T, WordCache C, RowAr
                             mk |= (uint32_t)(x[k] != T.pad) << (8 * k);
                         }
                         v = make_int4(x[0], x[1], x[2], x[3]);
-                        if (generic_mask) tok_total += (uint32_t)__popc(mk);
+                        tok_total += (uint32_t)__popc(mk);
                     }
                     st_cs128(A.ids + dr * W + i0, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
                     if (A.mask) st_cs32(A.mask + dr * W + i0, mk);
