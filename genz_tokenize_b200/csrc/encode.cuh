@@ -50,6 +50,10 @@ struct RowArgs {
     uint32_t* redo_list;       // rows with cache misses (filled in pass 1)
     uint32_t* fix_list;        // rows whose token types need the generic kernel
     int8_t eos_i8;
+    // return_offset=True (tokenize.py:105-117,225-234): words per side (COUNT writes), span table (RAGGED writes)
+    int32_t* nwA; int32_t* nwB;
+    const int64_t* span_off;   // [n_rows+1] first span entry of each row
+    int32_t* spans;            // [entries][2]
 };
 
 static const int WIN_LANES = 30;            // pieces whose word starts a window handles; 2 more are look-ahead
@@ -68,6 +72,9 @@ struct __align__(16) TileSmem {
     uint32_t dflag[32];        // F_*
     int32_t dkeep[32];         // RAGGED: tokens to keep
     uint32_t bnd[32];          // document-start bits per piece of the current window
+    int64_t dsbase[32];        // spans: index of this side's first entry for the row
+    int32_t dshift[32];        // spans: added to a framed token position to get the reference's numbering
+    int32_t dwrd[32];          // words met so far in this side
     SeqDesc dsd[32];           // FIXED pairs: token-type description per row
     uint32_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown) | document << 16
 };
@@ -300,7 +307,7 @@ __device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t
 // position of every row.  Tokens at positions < limit are delivered to rowbufs (FIXED) / ts->dout (RAGGED).
 template <int MODE>
 __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ bytes, TileSmem* ts, int nd,
-                                          int lane, int32_t limit, int32_t* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok) {
+                                          int lane, int32_t limit, int32_t* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
     const int64_t S = ts->doff[0], E = ts->doff[nd];
     // documents that are empty share their start with the next one: then the per-piece start bits cannot number
     // documents and every word finds its document by binary search instead
@@ -406,8 +413,23 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             // q is a lower bound of the word's position while earlier words are pending: if even that is past the
             // row's end the word is irrelevant, otherwise the row must be redone after k_bpe_pending
             if (pending && q < limit) atomicOr(&ts->dflag[doc], F_DIRTY);
+            int wrank = 0, wbase_idx = 0;
+            if (MODE != MODE_FIXED && count_words) {                     // word index inside the row (return_offset)
+                const int dprev = __shfl_up_sync(FULL_MASK, doc, 1);
+                const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0 || dprev != doc);
+                wrank = lane - (31 - __clz(heads & ((2u << lane) - 1)));
+                if (has) wbase_idx = ts->dwrd[doc];
+            }
             __syncwarp();
-            if (has && (lane == 31 || dnext != doc)) ts->dpos[doc] = q + (int32_t)nt;
+            if (has && (lane == 31 || dnext != doc)) {
+                ts->dpos[doc] = q + (int32_t)nt;
+                if (MODE != MODE_FIXED && count_words) ts->dwrd[doc] = wbase_idx + wrank + 1;
+            }
+            if (MODE == MODE_RAGGED && spans && has) {                   // (first, last) token of the word, tokenize.py:112-113
+                int32_t* e = spans + 2 * (ts->dsbase[doc] + 1 + wbase_idx + wrank);
+                e[0] = q + ts->dshift[doc];
+                e[1] = q + (int32_t)nt - 1 + ts->dshift[doc];
+            }
             if (MODE != MODE_COUNT && has && nt) {
                 int32_t* dst; int32_t lim;
                 if (MODE == MODE_FIXED) { dst = rowbufs + (size_t)doc * Wp; lim = limit; }
@@ -464,9 +486,12 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         // ---- set up the tile
         if (lane < nd) ts->doff[lane] = A.a.off[r0 + lane];
         if (lane == 0) ts->doff[nd] = A.a.off[r0 + nd];            // nd may be 32: 33 offsets
+        const bool count_words = MODE != MODE_FIXED && ((MODE == MODE_COUNT && A.nwA) || (MODE == MODE_RAGGED && A.spans));
         if (lane < nd) {
             ts->dpos[lane] = 1;                                    // position 0 is <s> (tokenize.py:135)
             ts->dflag[lane] = 0;
+            ts->dwrd[lane] = 0;
+            if (MODE == MODE_RAGGED && A.spans) { ts->dsbase[lane] = A.span_off[r0 + lane]; ts->dshift[lane] = 0; }
             if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = T.bos; }
             if (MODE == MODE_RAGGED) {
                 const int64_t ro = A.row_off[r0 + lane];
@@ -476,7 +501,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             }
         }
         __syncwarp();
-        walk_side<MODE>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok);
+        walk_side<MODE>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         if (A.has_pair) {
             // ... </s> </s> B   (tokenize.py:237-239)
             if (lane < nd) {
@@ -485,12 +510,28 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 if (MODE == MODE_FIXED) { int32_t* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = T.eos; if (pos + 1 < limit) rb[pos + 1] = T.eos; }
                 if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->dout[lane]; const int32_t kp = ts->dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
                 ts->dpos[lane] = pos + 2;
+                if (count_words) {
+                    const int32_t nw = ts->dwrd[lane];
+                    if (MODE == MODE_COUNT) A.nwA[r0 + lane] = nw;
+                    if (MODE == MODE_RAGGED) {
+                        // offset = [(0,0)] + words + [(n+1,n+1)] for A (tokenize.py:105,116); B's entries follow, every
+                        // value shifted by the NUMBER OF ENTRIES of A (tokenize.py:232-233)
+                        int32_t* e = A.spans + 2 * ts->dsbase[lane];
+                        e[0] = 0; e[1] = 0;
+                        e[2 * (nw + 1)] = pos; e[2 * (nw + 1) + 1] = pos;           // n+1 with n = pos-1 tokens
+                        ts->dsbase[lane] += nw + 2;
+                        ts->dshift[lane] = (nw + 2) - (pos + 2) + 1;             // B token at framed q -> (q - (pos+2) + 1) + (nw+2)
+                        int32_t* f = A.spans + 2 * ts->dsbase[lane];
+                        f[0] = nw + 2; f[1] = nw + 2;
+                    }
+                    ts->dwrd[lane] = 0;
+                }
             }
             __syncwarp();
             if (lane < nd) ts->doff[lane] = A.b.off[r0 + lane];
             if (lane == 0) ts->doff[nd] = A.b.off[r0 + nd];
             __syncwarp();
-            walk_side<MODE>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok);
+            walk_side<MODE>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         }
         // ---- closing </s>, row bookkeeping (one lane per row)
         if (lane < nd) {
@@ -516,6 +557,16 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 }
             }
             if (MODE == MODE_COUNT) A.L[r0 + lane] = dL;
+            if (count_words) {
+                const int32_t nw = ts->dwrd[lane];
+                if (MODE == MODE_COUNT) { if (A.has_pair) A.nwB[r0 + lane] = nw; else A.nwA[r0 + lane] = nw; }
+                if (MODE == MODE_RAGGED) {
+                    int32_t* e = A.spans + 2 * ts->dsbase[lane];
+                    if (!A.has_pair) { e[0] = 0; e[1] = 0; }
+                    const int32_t tail = pos + ts->dshift[lane];                    // (n+1) of this side in the reference's numbering
+                    e[2 * (nw + 1)] = tail; e[2 * (nw + 1) + 1] = tail;
+                }
+            }
         }
         __syncwarp();
         if (MODE != MODE_FIXED) continue;

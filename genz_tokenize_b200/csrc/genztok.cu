@@ -65,7 +65,7 @@ struct DeviceCtx {
     // chunk workspace
     DevBuf text, toff, pair, poff;                // inputs
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
-    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc;
+    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
     // profiling
     bool profiling = false;
@@ -387,7 +387,7 @@ void genztok_destroy(genztok_t* h) {
         if (d->stream) cudaStreamSynchronize(d->stream);
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
-                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->slots,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->slots,
                           &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -544,7 +544,6 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
     if (!h) return GENZTOK_E_INVALID;
     if (!out || n < 0 || !text_off) return fail(h, GENZTOK_E_INVALID, "genztok_encode: bad arguments");
     if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
-    if (flags & GENZTOK_WANT_SPANS) return fail(h, GENZTOK_E_INVALID, "spans: not implemented yet");
     memset(out, 0, sizeof *out);
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceCtx* d = h->devs[0];
@@ -553,7 +552,8 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
     LaunchScope::cur_stream = st;
     const bool has_pair = pair_off != nullptr;
     const bool has_max_len = max_len != GENZTOK_MAX_LEN_NONE;
-    const bool fixed = has_max_len && max_len >= 1 && padding && truncation && fixed_fits(d, max_len);
+    const bool want_spans = (flags & GENZTOK_WANT_SPANS) != 0;       // return_offset: produced by the ragged pipeline
+    const bool fixed = has_max_len && max_len >= 1 && padding && truncation && fixed_fits(d, max_len) && !want_spans;
     const int8_t eos8 = eos_as_i8(d);
     OutBlock* ob = new OutBlock();
     out->_owner = ob;
@@ -596,7 +596,9 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
 
     // ragged accumulators (host, pageable)
     std::vector<int32_t> r_ids; std::vector<uint8_t> r_mask; std::vector<int8_t> r_tt, r_seq;
-    std::vector<int64_t> r_off;
+    std::vector<int32_t> r_spans;
+    if (want_spans) { out->span_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->span_off); out->span_off[0] = 0; }
+    int64_t span_total = 0;
     if (fixed) {
         const size_t tot = (size_t)n * (size_t)max_len;
         out->width = max_len; out->total = (int64_t)tot;
@@ -672,23 +674,35 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         RowArgs A{};
         A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = flags;
         A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8;
+        if (want_spans) {
+            CUF(d->nwA.ensure((size_t)m * 4)); CUF(d->nwB.ensure((size_t)m * 4)); CUF(d->span_cnt.ensure((size_t)m * 8)); CUF(d->span_off.ensure((size_t)(m + 1) * 8));
+            A.nwA = d->nwA.as<int32_t>(); A.nwB = d->nwB.as<int32_t>();
+        }
         A.D = pick_tile_docs(h, d, tb, pb, m, 0, false);
         FAIL_RC(launch_rows<MODE_COUNT>(h, d, A, st, "k_rows_count", m));
         FAIL_RC(launch_bpe(h, d, st));
         RowArgs R = A; R.row_list = d->redo.as<uint32_t>();
         FAIL_RC(launch_rows<MODE_COUNT>(h, d, R, st, "k_rows_count_redo", std::min<int64_t>(m, (int64_t)d->sm_count * 64)));
         LenArgs LA{d->L.as<int32_t>(), m, (int32_t)has_max_len, has_max_len ? max_len : 0, padding ? 1 : 0, truncation ? 1 : 0,
-                   d->keep.as<int32_t>(), d->out_len.as<int64_t>(), d->tail.as<uint8_t>()};
+                   d->keep.as<int32_t>(), d->out_len.as<int64_t>(), d->tail.as<uint8_t>(),
+                   want_spans ? d->nwA.as<int32_t>() : nullptr, (want_spans && has_pair) ? d->nwB.as<int32_t>() : nullptr,
+                   want_spans ? d->span_cnt.as<int64_t>() : nullptr};
         { LaunchScope ls(h, d, "k_row_lens"); k_row_lens<<<(unsigned)std::min<int64_t>((m + 255) / 256, 4096), 256, 0, st>>>(LA); }
         { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), m); }
-        int64_t total = 0;
+        int64_t total = 0, span_n = 0;
+        if (want_spans) {
+            { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->span_cnt.as<int64_t>(), d->span_off.as<int64_t>(), m); }
+            CUF(cudaMemcpyAsync(&span_n, d->span_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st));
+        }
         CUF(cudaMemcpyAsync(&total, d->row_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st));
         CUF(cudaStreamSynchronize(st));
+        if (want_spans) CUF(d->spans.ensure((size_t)span_n * 8 + 16));
         CUF(d->ids.ensure((size_t)total * 4 + 16)); CUF(d->mask.ensure((size_t)total + 16)); CUF(d->row_len.ensure((size_t)m * 4));
         if (has_pair) { CUF(d->tt.ensure((size_t)total + 16)); CUF(d->seq.ensure((size_t)total + 16)); CUF(d->seq_len.ensure((size_t)m * 4)); CUF(d->tt_len.ensure((size_t)m * 4)); CUF(d->status.ensure((size_t)m)); }
         { LaunchScope ls(h, d, "k_reset_lists"); k_reset_lists<<<1, 1, 0, st>>>(d->C); }
         RowArgs E = A;
         E.ids = d->ids.as<int32_t>(); E.row_off = d->row_off.as<int64_t>(); E.keep = d->keep.as<int32_t>();
+        if (want_spans) { E.span_off = d->span_off.as<int64_t>(); E.spans = d->spans.as<int32_t>(); }
         FAIL_RC(launch_rows<MODE_RAGGED>(h, d, E, st, "k_rows_ragged", m));
         PostArgs Q{};
         Q.ids = d->ids.as<int32_t>(); Q.row_off = d->row_off.as<int64_t>(); Q.n_rows = m; Q.keep = d->keep.as<int32_t>(); Q.tail = d->tail.as<uint8_t>();
@@ -711,6 +725,14 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
                 CUF(cudaMemcpyAsync(r_seq.data() + old, d->seq.p, (size_t)total, cudaMemcpyDeviceToHost, st));
             }
         }
+        std::vector<int64_t> soffs;
+        if (want_spans) {
+            soffs.resize((size_t)m + 1);
+            const size_t so = r_spans.size();
+            r_spans.resize(so + (size_t)span_n * 2);
+            if (span_n) CUF(cudaMemcpyAsync(r_spans.data() + so, d->spans.p, (size_t)span_n * 8, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(soffs.data(), d->span_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
         CUF(cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         CUF(cudaMemcpyAsync(out->row_len + r0, d->row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
         if (has_pair) {
@@ -721,6 +743,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         CUF(cudaStreamSynchronize(st));
         for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = ragged_total + offs[(size_t)i];
         ragged_total += total;
+        if (want_spans) { for (int64_t i = 1; i <= m; i++) out->span_off[r0 + i] = span_total + soffs[(size_t)i]; span_total += span_n; }
     }
     unsigned long long tokens_after = 0, nerr = 0;
     CUF(cudaMemcpyAsync(&tokens_after, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
@@ -741,6 +764,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         };
         keepv(r_ids, &out->input_ids); keepv(r_mask, &out->attention_mask);
         if (has_pair) { keepv(r_tt, &out->token_type_ids); keepv(r_seq, &out->sequence_id); }
+        if (want_spans) keepv(r_spans, &out->spans);
     }
     return GENZTOK_OK;
 #undef OOM_CHECK

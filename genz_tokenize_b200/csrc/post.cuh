@@ -19,6 +19,8 @@ struct LenArgs {
     int32_t* keep;         // framed tokens copied
     int64_t* out_len;      // final row length
     uint8_t* tail;         // 0 none, 1 pad fill [keep, out_len), 2 eos at keep
+    const int32_t* nwA; const int32_t* nwB;   // return_offset: words per side (NULL when not wanted)
+    int64_t* span_cnt;     // entries of the row's offset list: (nwA + 2) [+ (nwB + 2)]
 };
 
 __global__ void k_row_lens(LenArgs A) {
@@ -30,6 +32,7 @@ __global__ void k_row_lens(LenArgs A) {
             else if (A.truncation) { keep = py_head(L, (int64_t)A.max_len - 1); out = keep + 1; tail = 2; }   // :144-145
         }
         A.keep[r] = (int32_t)keep; A.out_len[r] = out; A.tail[r] = tail;
+        if (A.span_cnt) A.span_cnt[r] = (int64_t)A.nwA[r] + 2 + (A.nwB ? (int64_t)A.nwB[r] + 2 : 0);
     }
 }
 

@@ -231,6 +231,8 @@ class Tokenize(object):
 
     def encode(self, sentence, return_offset):
         """tokenize.py:126-135"""
+        if not isinstance(sentence, str):
+            raise TypeError("expected string or bytes-like object, got %r" % type(sentence).__name__)
         r = self._encode_raw([sentence], None, None, True, True, 0, return_offset)
         ids = r["input_ids"].tolist()
         if return_offset:

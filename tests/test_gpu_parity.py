@@ -35,7 +35,20 @@ def test_readme_vector(tok, golden):
 
 
 def test_corner_calls(tok, golden):
-    check_cases(tok, no_offset(golden["calls"]), "calls")
+    check_cases(tok, golden["calls"], "calls")      # includes return_offset=True cases
+
+
+def test_return_offset_batch_vs_oracle(tok, oracle):
+    from genz_tokenize_b200 import workload
+    for seed, paired, kw in [(501, True, dict(max_len=12)), (502, False, dict()), (503, True, dict())]:
+        t = workload.generate(seed, 1200, 0, 12, 0.1)
+        p = workload.generate(seed + 5000, 1200, 0, 12, 0.1) if paired else None
+        be = tok.encode_batch(t, p, return_offset=True, **kw)
+        orc = oracle.encode_batch(t, p, return_offset=True, threads=8, **kw)
+        assert np.array_equal(be["span_off"], orc["span_off"]), seed
+        assert np.array_equal(be["spans"], orc["span"]), seed
+        assert np.array_equal(be["input_ids"], orc["ids"]), seed
+    assert tok.encode("xin chào\n các bạn", True) == ([1, 217, 30075, 1742, 4, 35, 175, 2], [(0, 0), (1, 1), (2, 4), (5, 5), (6, 6), (7, 7)])
 
 
 def test_random_rows_single_calls(tok, golden):
