@@ -64,19 +64,24 @@ static const uint32_t F_DIRTY = 1u, F_SPECIAL = 2u, F_PADTOK = 4u;
 struct SeqDesc { int32_t p1, m, f1, f2, r1, r2, err; };
 
 // per-warp shared memory (the D token rows follow for MODE_FIXED)
+struct RaggedTile {            // MODE_COUNT / MODE_RAGGED only
+    int64_t dout[32];          // row start in ids
+    int64_t dsbase[32];        // spans: index of this side's first entry for the row
+    int32_t dkeep[32];         // tokens to keep
+    int32_t dshift[32];        // spans: added to a framed token position to get the reference's numbering
+    int32_t dwrd[32];          // words met so far in this side
+};
 struct __align__(16) TileSmem {
     int64_t doff[33];          // document offsets of the tile for the side being walked
-    int64_t dout[32];          // RAGGED: row start in ids
     int32_t dpos[32];          // next token position per document
     int32_t dnA[32];           // tokens of side A per document
     uint32_t dflag[32];        // F_*
-    int32_t dkeep[32];         // RAGGED: tokens to keep
     uint32_t bnd[32];          // document-start bits per piece of the current window
-    int64_t dsbase[32];        // spans: index of this side's first entry for the row
-    int32_t dshift[32];        // spans: added to a framed token position to get the reference's numbering
-    int32_t dwrd[32];          // words met so far in this side
-    SeqDesc dsd[32];           // FIXED pairs: token-type description per row
     uint32_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown) | document << 16
+    union {                    // keeps 4 blocks of 8 warps per SM at max_len 128
+        SeqDesc dsd[32];       // MODE_FIXED pairs: token-type description per row
+        RaggedTile rg;
+    };
 };
 
 // ---- byte classification -----------------------------------------------------------------------
@@ -418,22 +423,22 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                 const int dprev = __shfl_up_sync(FULL_MASK, doc, 1);
                 const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0 || dprev != doc);
                 wrank = lane - (31 - __clz(heads & ((2u << lane) - 1)));
-                if (has) wbase_idx = ts->dwrd[doc];
+                if (has) wbase_idx = ts->rg.dwrd[doc];
             }
             __syncwarp();
             if (has && (lane == 31 || dnext != doc)) {
                 ts->dpos[doc] = q + (int32_t)nt;
-                if (MODE != MODE_FIXED && count_words) ts->dwrd[doc] = wbase_idx + wrank + 1;
+                if (MODE != MODE_FIXED && count_words) ts->rg.dwrd[doc] = wbase_idx + wrank + 1;
             }
             if (MODE == MODE_RAGGED && spans && has) {                   // (first, last) token of the word, tokenize.py:112-113
-                int32_t* e = spans + 2 * (ts->dsbase[doc] + 1 + wbase_idx + wrank);
-                e[0] = q + ts->dshift[doc];
-                e[1] = q + (int32_t)nt - 1 + ts->dshift[doc];
+                int32_t* e = spans + 2 * (ts->rg.dsbase[doc] + 1 + wbase_idx + wrank);
+                e[0] = q + ts->rg.dshift[doc];
+                e[1] = q + (int32_t)nt - 1 + ts->rg.dshift[doc];
             }
             if (MODE != MODE_COUNT && has && nt) {
                 int32_t* dst; int32_t lim;
                 if (MODE == MODE_FIXED) { dst = rowbufs + (size_t)doc * Wp; lim = limit; }
-                else { dst = ids_out + ts->dout[doc]; lim = ts->dkeep[doc]; }
+                else { dst = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }
                 uint32_t fl = 0;
                 if (nt == 1) {
                     const int32_t t = (int32_t)(val & VAL_PAYLOAD);
@@ -490,13 +495,13 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         if (lane < nd) {
             ts->dpos[lane] = 1;                                    // position 0 is <s> (tokenize.py:135)
             ts->dflag[lane] = 0;
-            ts->dwrd[lane] = 0;
-            if (MODE == MODE_RAGGED && A.spans) { ts->dsbase[lane] = A.span_off[r0 + lane]; ts->dshift[lane] = 0; }
+            ts->rg.dwrd[lane] = 0;
+            if (MODE == MODE_RAGGED && A.spans) { ts->rg.dsbase[lane] = A.span_off[r0 + lane]; ts->rg.dshift[lane] = 0; }
             if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = T.bos; }
             if (MODE == MODE_RAGGED) {
                 const int64_t ro = A.row_off[r0 + lane];
                 const int32_t kp = A.keep[r0 + lane];
-                ts->dout[lane] = ro; ts->dkeep[lane] = kp;
+                ts->rg.dout[lane] = ro; ts->rg.dkeep[lane] = kp;
                 if (kp > 0) A.ids[ro] = T.bos;
             }
         }
@@ -508,23 +513,23 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 const int32_t pos = ts->dpos[lane];
                 ts->dnA[lane] = pos - 1;
                 if (MODE == MODE_FIXED) { int32_t* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = T.eos; if (pos + 1 < limit) rb[pos + 1] = T.eos; }
-                if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->dout[lane]; const int32_t kp = ts->dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
+                if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->rg.dout[lane]; const int32_t kp = ts->rg.dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
                 ts->dpos[lane] = pos + 2;
                 if (count_words) {
-                    const int32_t nw = ts->dwrd[lane];
+                    const int32_t nw = ts->rg.dwrd[lane];
                     if (MODE == MODE_COUNT) A.nwA[r0 + lane] = nw;
                     if (MODE == MODE_RAGGED) {
                         // offset = [(0,0)] + words + [(n+1,n+1)] for A (tokenize.py:105,116); B's entries follow, every
                         // value shifted by the NUMBER OF ENTRIES of A (tokenize.py:232-233)
-                        int32_t* e = A.spans + 2 * ts->dsbase[lane];
+                        int32_t* e = A.spans + 2 * ts->rg.dsbase[lane];
                         e[0] = 0; e[1] = 0;
                         e[2 * (nw + 1)] = pos; e[2 * (nw + 1) + 1] = pos;           // n+1 with n = pos-1 tokens
-                        ts->dsbase[lane] += nw + 2;
-                        ts->dshift[lane] = (nw + 2) - (pos + 2) + 1;             // B token at framed q -> (q - (pos+2) + 1) + (nw+2)
-                        int32_t* f = A.spans + 2 * ts->dsbase[lane];
+                        ts->rg.dsbase[lane] += nw + 2;
+                        ts->rg.dshift[lane] = (nw + 2) - (pos + 2) + 1;             // B token at framed q -> (q - (pos+2) + 1) + (nw+2)
+                        int32_t* f = A.spans + 2 * ts->rg.dsbase[lane];
                         f[0] = nw + 2; f[1] = nw + 2;
                     }
-                    ts->dwrd[lane] = 0;
+                    ts->rg.dwrd[lane] = 0;
                 }
             }
             __syncwarp();
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             const int32_t pos = ts->dpos[lane];
             const int32_t dL = pos + 1;                                // framed length (>= W when the walk stopped early)
             if (MODE == MODE_FIXED) { if (pos < limit) rowbufs[(size_t)lane * Wp + pos] = T.eos; }
-            if (MODE == MODE_RAGGED) { if (pos < ts->dkeep[lane]) A.ids[ts->dout[lane] + pos] = T.eos; }
+            if (MODE == MODE_RAGGED) { if (pos < ts->rg.dkeep[lane]) A.ids[ts->rg.dout[lane] + pos] = T.eos; }
             const uint32_t fl = ts->dflag[lane];
             if (fl & F_DIRTY) {
                 if (!A.row_list) { const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL); A.redo_list[k] = (uint32_t)(r0 + lane); }
@@ -558,12 +563,12 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             }
             if (MODE == MODE_COUNT) A.L[r0 + lane] = dL;
             if (count_words) {
-                const int32_t nw = ts->dwrd[lane];
+                const int32_t nw = ts->rg.dwrd[lane];
                 if (MODE == MODE_COUNT) { if (A.has_pair) A.nwB[r0 + lane] = nw; else A.nwA[r0 + lane] = nw; }
                 if (MODE == MODE_RAGGED) {
-                    int32_t* e = A.spans + 2 * ts->dsbase[lane];
+                    int32_t* e = A.spans + 2 * ts->rg.dsbase[lane];
                     if (!A.has_pair) { e[0] = 0; e[1] = 0; }
-                    const int32_t tail = pos + ts->dshift[lane];                    // (n+1) of this side in the reference's numbering
+                    const int32_t tail = pos + ts->rg.dshift[lane];                    // (n+1) of this side in the reference's numbering
                     e[2 * (nw + 1)] = tail; e[2 * (nw + 1) + 1] = tail;
                 }
             }
