@@ -59,6 +59,7 @@ struct RowArgs {
 static const int WIN_LANES = 30;            // pieces whose word starts a window handles; 2 more are look-ahead
 static const int WLIST_CAP = WIN_LANES * 8; // at most 8 word starts per 16-byte piece
 static const uint32_t F_DIRTY = 1u, F_SPECIAL = 2u, F_PADTOK = 4u;
+static const uint32_t EM_LEN = 0xFFFFFu, EM_TRUNC = 1u << 20, EM_GENERIC = 1u << 21, EM_SKIP = 1u << 22;
 
 // get_sequence_id + get_token_type in closed form for one row (see seq_describe)
 struct SeqDesc { int32_t p1, m, f1, f2, r1, r2, err; };
@@ -76,6 +77,7 @@ struct __align__(16) TileSmem {
     int32_t dpos[32];          // next token position per document
     int32_t dnA[32];           // tokens of side A per document
     uint32_t dflag[32];        // F_*
+    uint32_t demit[32];        // FIXED: row length | EM_* for the write-out loop
     uint32_t bnd[32];          // document-start bits per piece of the current window
     uint32_t wlist[WLIST_CAP]; // word starts: position in window (9 bits) | bytes to first whitespace (7 bits, 0 = unknown) | document << 16
     union {                    // keeps 4 blocks of 8 warps per SM at max_len 128
@@ -102,6 +104,12 @@ __device__ __forceinline__ uint32_t ws_lead4(uint32_t w) {
     uint32_t lo = w & 0x7F7F7F7Fu;                // 0xC2 -> 0x42, 0xE1..0xE3 -> 0x61..0x63
     uint32_t ge42 = lo + 0x3E3E3E3Eu, ge43 = lo + 0x3D3D3D3Du, ge61 = lo + 0x1F1F1F1Fu, ge64 = lo + 0x1C1C1C1Cu;
     return ((ge42 & ~ge43) | (ge61 & ~ge64)) & w & 0x80808080u;
+}
+// bytes 0x80..0xA0: every second byte of a non-ASCII whitespace (80, 81, 85, 9A, A0) is one -> 0x80 flags.
+// (Vietnamese letters are E1 BA/BB xx, C3 xx, C4 xx, C6 xx: their E1 leads fail this test on the next byte.)
+__device__ __forceinline__ uint32_t ws_second4(uint32_t w) {
+    uint32_t lo = w & 0x7F7F7F7Fu;
+    return ~(lo + 0x5F5F5F5Fu) & w & 0x80808080u;   // high bit set and low 7 bits <= 0x20
 }
 
 __device__ __forceinline__ uint32_t byte_of(const uint4& w, int j) {
@@ -146,12 +154,16 @@ __device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* by
     if ((w.x | w.y | w.z | w.w) & 0x80808080u) {
         uint32_t lead = gather_msb(ws_lead4(w.x)) | (gather_msb(ws_lead4(w.y)) << 4) | (gather_msb(ws_lead4(w.z)) << 8) |
                         (gather_msb(ws_lead4(w.w)) << 12);
-        lead &= inseg;
-        while (lead) {
-            const int j = __ffs(lead) - 1;
-            lead &= lead - 1;
-            const int l = multibyte_ws(byte_of(w, j), bytes, a + j, E);
-            if (l && a + j + l <= doff[doc_of(doff, nd, a + j) + 1]) ws |= ((1u << l) - 1) << j;
+        if (lead) {
+            const uint32_t sec = gather_msb(ws_second4(w.x)) | (gather_msb(ws_second4(w.y)) << 4) | (gather_msb(ws_second4(w.z)) << 8) |
+                                 (gather_msb(ws_second4(w.w)) << 12);
+            lead &= inseg & ((sec >> 1) | 0x8000u);       // the byte after the lead must qualify (unknown for byte 15)
+            while (lead) {
+                const int j = __ffs(lead) - 1;
+                lead &= lead - 1;
+                const int l = multibyte_ws(byte_of(w, j), bytes, a + j, E);
+                if (l && a + j + l <= doff[doc_of(doff, nd, a + j) + 1]) ws |= ((1u << l) - 1) << j;
+            }
         }
     }
     return (ws & 0x3FFFFu) | (~inseg & 0xFFFFu);
@@ -476,17 +488,17 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
     TileSmem* ts = reinterpret_cast<TileSmem*>(smem_raw + (size_t)wib * per_warp);
     int32_t* rowbufs = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ts) + sizeof(TileSmem));
 
-    const unsigned long long n_items = A.row_list ? C.ctr[C_REDO] : (unsigned long long)A.n_rows;
+    const uint32_t n_items = (uint32_t)(A.row_list ? C.ctr[C_REDO] : (unsigned long long)A.n_rows);   // rows per chunk < 2^31
     // a row list holds arbitrary rows: they are not contiguous in the text, so its tiles hold one document
-    const unsigned long long Dt = A.row_list ? 1ull : (unsigned long long)D;
-    const unsigned long long n_tiles = (n_items + Dt - 1) / Dt;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * wpb;
+    const uint32_t Dt = A.row_list ? 1u : (uint32_t)D;
+    const uint32_t n_tiles = (n_items + Dt - 1) / Dt;
+    const uint32_t n_warps = gridDim.x * (uint32_t)wpb;
     const int32_t limit = MODE == MODE_FIXED ? W - 1 : 0x7FFFFFFF;
     const bool insert_ok = !A.row_list && MODE != MODE_RAGGED;   // second passes only look words up
     uint32_t tok_total = 0;
-    for (unsigned long long tile = (unsigned long long)blockIdx.x * wpb + wib; tile < n_tiles; tile += n_warps) {
+    for (uint32_t tile = blockIdx.x * (uint32_t)wpb + wib; tile < n_tiles; tile += n_warps) {
         const int64_t r0 = A.row_list ? (int64_t)A.row_list[tile] : (int64_t)(tile * Dt);
-        const unsigned long long left = n_items - tile * Dt;
+        const uint32_t left = n_items - tile * Dt;
         const int nd = (int)(Dt < left ? Dt : left);
         // ---- set up the tile
         if (lane < nd) ts->doff[lane] = A.a.off[r0 + lane];
@@ -548,9 +560,11 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             if (fl & F_DIRTY) {
                 if (!A.row_list) { const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL); A.redo_list[k] = (uint32_t)(r0 + lane); }
                 else atomicAdd(&C.ctr[C_ERR], 1ULL);   // cannot happen: every word of a redo row was inserted in pass 1
+                if (MODE == MODE_FIXED) ts->demit[lane] = EM_SKIP;
             } else if (MODE == MODE_FIXED) {
                 const int64_t dr = r0 + lane;
                 const int32_t Lr = dL < W ? dL : W;
+                ts->demit[lane] = (uint32_t)Lr | (dL >= W ? EM_TRUNC : 0u) | ((fl & F_PADTOK) ? EM_GENERIC : 0u);
                 if (A.row_len) A.row_len[dr] = Lr;
                 if (!(fl & F_PADTOK)) tok_total += (uint32_t)Lr;       // rows with a pad id inside are counted from their mask
                 if (A.has_pair) {
@@ -576,46 +590,55 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         __syncwarp();
         if (MODE != MODE_FIXED) continue;
         // ---- FIXED: the warp writes its rows -----------------------------------------------------------
-        for (int d = 0; d < nd; d++) {
-            const uint32_t fl = ts->dflag[d];
-            if (fl & F_DIRTY) continue;
-            const int64_t dr = r0 + d;
-            const int32_t dL = ts->dpos[d] + 1;
-            const int32_t Lr = dL < W ? dL : W;
-            const bool trunc = dL >= W;
-            const bool generic_mask = (fl & F_PADTOK) != 0;
-            const int32_t* rb = rowbufs + (size_t)d * Wp;
-            if ((W & 15) == 0) {
-                for (int32_t i0 = lane * 4; i0 < W; i0 += 128) {
-                    int4 v = *reinterpret_cast<const int4*>(rb + i0);
+        if ((W & 15) == 0) {
+            // lane <-> quad column; rows of the tile in the inner loop so that everything but the row length is hoisted
+            for (int32_t i0 = lane * 4; i0 < W; i0 += 128) {
+                const bool lastq = i0 + 4 == W;
+                const size_t g0 = (size_t)r0 * (size_t)W + (size_t)i0;
+                int32_t* gi = A.ids + g0;
+                uint8_t* gm = A.mask ? A.mask + g0 : nullptr;
+                int8_t* gt = (A.has_pair && A.tt) ? A.tt + g0 : nullptr;
+                int8_t* gs = (A.has_pair && A.seq) ? A.seq + g0 : nullptr;
+                const int32_t* rb = rowbufs + i0;
+                for (int d = 0; d < nd; d++, gi += W, rb += Wp) {
+                    const uint32_t em = ts->demit[d];
+                    if (em & EM_SKIP) continue;
+                    const int32_t c = (int32_t)(em & EM_LEN) - i0;      // real tokens from this quad on
+                    int4 v = *reinterpret_cast<const int4*>(rb);
                     uint32_t mk;
-                    if (!generic_mask) {
-                        const int32_t c = Lr - i0;                      // real tokens in this quad: branch-free select
+                    if (!(em & EM_GENERIC)) {
                         v.x = c > 0 ? v.x : T.pad; v.y = c > 1 ? v.y : T.pad; v.z = c > 2 ? v.z : T.pad; v.w = c > 3 ? v.w : T.pad;
-                        if (trunc && i0 + 4 == W) v.w = T.eos;
+                        if (lastq && (em & EM_TRUNC)) v.w = T.eos;
                         mk = c >= 4 ? 0x01010101u : (c <= 0 ? 0u : (0x01010101u & ((1u << (8 * c)) - 1)));
                     } else {                                            // a pad id inside the text: mask by value
                         int32_t x[4] = {v.x, v.y, v.z, v.w};
                         mk = 0;
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const int32_t i = i0 + k;
-                            x[k] = i < Lr ? ((trunc && i == W - 1) ? T.eos : x[k]) : T.pad;
+                            x[k] = k < c ? ((lastq && k == 3 && (em & EM_TRUNC)) ? T.eos : x[k]) : T.pad;
                             mk |= (uint32_t)(x[k] != T.pad) << (8 * k);
                         }
                         v = make_int4(x[0], x[1], x[2], x[3]);
                         tok_total += (uint32_t)__popc(mk);
                     }
-                    st_cs128(A.ids + dr * W + i0, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
-                    if (A.mask) st_cs32(A.mask + dr * W + i0, mk);
-                    if (A.has_pair && (A.tt || A.seq)) {
+                    st_cs128(gi, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
+                    if (gm) st_cs32(gm + (size_t)d * W, mk);
+                    if (gt || gs) {
                         uint32_t ttw, sqw;
                         seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
-                        if (A.tt) st_cs32(A.tt + dr * W + i0, ttw);
-                        if (A.seq) st_cs32(A.seq + dr * W + i0, sqw);
+                        if (gt) st_cs32(gt + (size_t)d * W, ttw);
+                        if (gs) st_cs32(gs + (size_t)d * W, sqw);
                     }
                 }
-            } else {
+            }
+        } else {
+            for (int d = 0; d < nd; d++) {
+                const uint32_t em = ts->demit[d];
+                if (em & EM_SKIP) continue;
+                const int64_t dr = r0 + d;
+                const int32_t Lr = (int32_t)(em & EM_LEN);
+                const bool trunc = (em & EM_TRUNC) != 0, generic_mask = (em & EM_GENERIC) != 0;
+                const int32_t* rb = rowbufs + (size_t)d * Wp;
                 for (int32_t i = lane; i < W; i += 32) {
                     const int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : rb[i]) : T.pad;
                     A.ids[dr * W + i] = t;
