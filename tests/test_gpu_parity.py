@@ -249,3 +249,60 @@ def test_config2_full_size_properties(tok, oracle):
     tok2.set_option("max_chunk_bytes", 1 << 22)
     be2 = tok2.encode_batch((t[0][:t[1][200000]], t[1][:200001]), max_len=128)
     assert hashlib.sha256(be2["input_ids"].tobytes()).hexdigest() == hashlib.sha256(ids[:200000].tobytes()).hexdigest()
+
+
+def _custom_model(td, n_words=4000, seed=77):
+    """BASELINE configs[4]: a custom vocab / bpe.codes made of concatenations of bundled words, with learned-looking merges."""
+    from genz_tokenize_b200 import workload
+    rng = np.random.default_rng(seed)
+    wl = workload.default_wordlist()
+    base = [wl.words[int(i)] for i in rng.integers(0, len(wl.words), size=n_words)]
+    words = list(dict.fromkeys(base + [a + "_" + b for a, b in zip(base[::2], base[1::2])]))
+    merges, seen, vocab = [], set(), {}
+    for w in words:                          # merges that build every word left to right, code point by code point
+        syms = list(w[:-1]) + [w[-1] + "</w>"]
+        cur = syms[0]
+        for s in syms[1:]:
+            if (cur, s) not in seen:
+                seen.add((cur, s))
+                merges.append("%s %s" % (cur, s))
+            cur = cur + s
+            vocab.setdefault(cur.replace("</w>", "") + ("" if cur.endswith("</w>") else "@@"), 1)
+        vocab[w] = 1
+    rng.shuffle(merges)
+    vp, mp = os.path.join(td, "vocab.txt"), os.path.join(td, "bpe.codes")
+    with open(vp, "w", encoding="utf-8") as f:
+        f.write("".join("%s %d\n" % (k, v) for k, v in vocab.items()))
+    with open(mp, "w", encoding="utf-8") as f:
+        f.write("#version: 0.2\n" + "\n".join(merges) + "\n")
+    return vp, mp, words
+
+
+def test_config5_custom_vocab_long_documents(oracle):
+    # fromFile with a large custom vocab / merge table, long documents with low word reuse, max_len=4096 (heavy truncation)
+    from genz_tokenize_b200 import Tokenize
+    from oracle.oracle import Oracle, pack_strings
+    with tempfile.TemporaryDirectory() as td:
+        vp, mp, words = _custom_model(td)
+        tok = Tokenize.fromFile(vp, mp)
+        orc = Oracle(vp, mp)
+        assert tok.vocab_size() == orc.vocab_size()
+        rng = np.random.default_rng(5)
+        docs = []
+        for i in range(48):
+            k = int(rng.integers(2000, 9000)) if i % 3 else int(rng.integers(0, 400))
+            ws = [words[int(j)] for j in rng.integers(0, len(words), size=k)]
+            for j in rng.integers(0, max(k, 1), size=k // 50):            # unseen material: unk, partial merges
+                ws[int(j)] = ws[int(j)][::-1] + "zq"
+            docs.append(" ".join(ws))
+        packed = pack_strings(docs)
+        for kw in (dict(max_len=4096), dict(max_len=512), dict()):
+            be = tok.encode_batch(packed, **kw)
+            ref = orc.encode_batch(packed, None, threads=8, **kw)
+            assert_matches_oracle(be, ref, what="config5 %r" % (kw,))
+        pairs = pack_strings(docs[::-1])
+        be = tok.encode_batch(packed, pairs, max_len=4096)
+        ref = orc.encode_batch(packed, pairs, max_len=4096, threads=8)
+        assert_matches_oracle(be, ref, what="config5 pairs")
+        dec = tok.decode_batch(be["input_ids"][:8])
+        assert dec == orc.decode_batch(be["input_ids"][:8].reshape(-1), np.arange(0, 8 * 4096 + 1, 4096, dtype=np.int64))
