@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--docs", type=int, default=N_DOCS, help="documents per GPU per step (default: the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the pair-encode and decode side measurements")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
@@ -249,8 +250,52 @@ def main():
         e2e_tokens = int(be["real_tokens"])
         del be
     lib.genztok_host_free(hp)
-    clocks = sampler.stop()
 
+    # ---- side measurements (N=1 only; reported under "extra", not the headline) ---------------------------
+    extra = None
+    if world == 1 and not args.no_extras:
+        extra = {}
+        peak0, _ = measured_hbm_peak()
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                flush.zero_(); fn()
+            torch.cuda.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, b in evs:
+                flush.zero_(); a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / reps
+
+        # decode of the [n,128] rows just produced (BASELINE configs[3] at one GPU's share)
+        holder = {}
+        ms = timed(lambda: holder.__setitem__("d", tok.decode_device(out["input_ids"])))
+        dbytes = int(holder["d"][0].numel())
+        dalg = 4 * n * MAX_LEN + dbytes + 8 * (n + 1)
+        extra["decode_padded_rows"] = {"rows_per_s": n / (ms * 1e-3), "ids_per_s": n * MAX_LEN / (ms * 1e-3), "ms": ms, "text_bytes": dbytes,
+                                       "alg_gb_per_s": dalg / (ms * 1e-3) / 1e9, "hbm_frac": dalg / (ms * 1e-3) / 1e9 / peak0,
+                                       "note": "includes the allocation of the text tensor and one device->host read of the total size"}
+        del holder
+        # sentence pairs, max_len=256, token types (BASELINE configs[2] at one GPU's share of 1,048,576 pairs)
+        pb_, po_ = workload.generate(SEED + 5000, n, 3, 13, 0.0)
+        pbytes = int(po_[-1])
+        d_pair = torch.from_numpy(np.concatenate([pb_, np.zeros((-pbytes) % 16 + 16, dtype=np.uint8)])).to(dev)
+        d_poff = torch.from_numpy(po_).to(dev)
+        W2 = 256
+        pout = {"input_ids": torch.empty((n, W2), dtype=torch.int32, device=dev), "attention_mask": torch.empty((n, W2), dtype=torch.uint8, device=dev),
+                "token_type_ids": torch.empty((n, W2), dtype=torch.int8, device=dev), "row_len": torch.empty((n,), dtype=torch.int32, device=dev),
+                "seq_len": torch.empty((n,), dtype=torch.int32, device=dev), "row_status": torch.empty((n,), dtype=torch.uint8, device=dev)}
+        tok2 = Tokenize(devices=[local_rank])
+        tok2.set_option("max_chunk_bytes", 1 << 27)       # both sides of 1M pairs (~106 MB) in one chunk
+        ms = timed(lambda: tok2.encode_device(d_text, d_off, d_pair, d_poff, max_len=W2, out=pout, text_bytes=in_bytes, pair_bytes=pbytes))
+        ptok = int(pout["row_len"].sum().item())
+        palg = in_bytes + pbytes + 16 * (n + 1) + n * W2 * 6
+        extra["encode_pairs_256"] = {"tokens_per_s": ptok / (ms * 1e-3), "pairs_per_s": n / (ms * 1e-3), "ms": ms, "input_gb_per_s": (in_bytes + pbytes) / (ms * 1e-3) / 1e9,
+                                     "alg_gb_per_s": palg / (ms * 1e-3) / 1e9, "hbm_frac": palg / (ms * 1e-3) / 1e9 / peak0,
+                                     "planes": "input_ids int32 + attention_mask uint8 + token_type_ids int8 [n,256]"}
+        del pout, d_pair, d_poff, tok2
+
+    clocks = sampler.stop()
     # ---- max over ranks --------------------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_ms, k_ms], dtype=torch.float64, device=dev)
     s = torch.tensor([tokens_per_step, in_bytes, launches, e2e_tokens], dtype=torch.float64, device=dev)
@@ -293,6 +338,8 @@ def main():
         "clocks": clocks,
         "kernels": prof,
     }
+    if extra is not None:
+        line["extra"] = extra
     if not args.no_cpu:
         threads = 0
         try:

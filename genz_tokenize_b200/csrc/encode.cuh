@@ -322,9 +322,9 @@ __device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t
 // ---- walking one side of a tile --------------------------------------------------------------------
 // All 32 lanes call this.  ts->doff[0..nd] holds the side's document offsets, ts->dpos[] the next token
 // position of every row.  Tokens at positions < limit are delivered to rowbufs (FIXED) / ts->dout (RAGGED).
-template <int MODE>
+template <int MODE, typename TokT>
 __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ bytes, TileSmem* ts, int nd,
-                                          int lane, int32_t limit, int32_t* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
+                                          int lane, int32_t limit, TokT* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
     const int64_t S = ts->doff[0], E = ts->doff[nd];
     // documents that are empty share their start with the next one: then the per-piece start bits cannot number
     // documents and every word finds its document by binary search instead
@@ -448,22 +448,22 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                 e[1] = q + (int32_t)nt - 1 + ts->rg.dshift[doc];
             }
             if (MODE != MODE_COUNT && has && nt) {
-                int32_t* dst; int32_t lim;
-                if (MODE == MODE_FIXED) { dst = rowbufs + (size_t)doc * Wp; lim = limit; }
-                else { dst = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }
+                TokT* dsts = nullptr; int32_t* dstg = nullptr; int32_t lim;
+                if (MODE == MODE_FIXED) { dsts = rowbufs + (size_t)doc * Wp; lim = limit; }
+                else { dstg = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }
                 uint32_t fl = 0;
                 if (nt == 1) {
                     const int32_t t = (int32_t)(val & VAL_PAYLOAD);
                     if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
                     if (t == T.pad) fl |= F_PADTOK;
-                    if (q < lim) dst[q] = t;
+                    if (q < lim) { if (MODE == MODE_FIXED) dsts[q] = (TokT)t; else dstg[q] = t; }
                 } else {
                     const uint32_t* src = C.tok_arena + (val & VAL_PAYLOAD) + 1;
                     for (uint32_t i = 0; i < nt && q < lim; i++, q++) {
                         const int32_t t = (int32_t)src[i];
                         if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
                         if (t == T.pad) fl |= F_PADTOK;
-                        dst[q] = t;
+                        if (MODE == MODE_FIXED) dsts[q] = (TokT)t; else dstg[q] = t;
                     }
                 }
                 if (fl) atomicOr(&ts->dflag[doc], fl);
@@ -478,15 +478,16 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
     __syncwarp();
 }
 
-template <int MODE>
+// TokT: type of the rows staged in shared memory (uint16_t when every id fits: half the footprint, twice the blocks)
+template <int MODE, typename TokT>
 __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D;
     const int32_t Wp = (W + 3) & ~3;
-    const size_t per_warp = sizeof(TileSmem) + (MODE == MODE_FIXED ? (size_t)D * Wp * 4 : 0);
+    const size_t per_warp = sizeof(TileSmem) + (MODE == MODE_FIXED ? (((size_t)D * Wp * sizeof(TokT) + 15) & ~(size_t)15) : 0);
     TileSmem* ts = reinterpret_cast<TileSmem*>(smem_raw + (size_t)wib * per_warp);
-    int32_t* rowbufs = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ts) + sizeof(TileSmem));
+    TokT* rowbufs = reinterpret_cast<TokT*>(reinterpret_cast<uint8_t*>(ts) + sizeof(TileSmem));
 
     const uint32_t n_items = (uint32_t)(A.row_list ? C.ctr[C_REDO] : (unsigned long long)A.n_rows);   // rows per chunk < 2^31
     // a row list holds arbitrary rows: they are not contiguous in the text, so its tiles hold one document
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             ts->dflag[lane] = 0;
             ts->rg.dwrd[lane] = 0;
             if (MODE == MODE_RAGGED && A.spans) { ts->rg.dsbase[lane] = A.span_off[r0 + lane]; ts->rg.dshift[lane] = 0; }
-            if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = T.bos; }
+            if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = (TokT)T.bos; }
             if (MODE == MODE_RAGGED) {
                 const int64_t ro = A.row_off[r0 + lane];
                 const int32_t kp = A.keep[r0 + lane];
@@ -518,13 +519,13 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             }
         }
         __syncwarp();
-        walk_side<MODE>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+        walk_side<MODE, TokT>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         if (A.has_pair) {
             // ... </s> </s> B   (tokenize.py:237-239)
             if (lane < nd) {
                 const int32_t pos = ts->dpos[lane];
                 ts->dnA[lane] = pos - 1;
-                if (MODE == MODE_FIXED) { int32_t* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = T.eos; if (pos + 1 < limit) rb[pos + 1] = T.eos; }
+                if (MODE == MODE_FIXED) { TokT* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = (TokT)T.eos; if (pos + 1 < limit) rb[pos + 1] = (TokT)T.eos; }
                 if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->rg.dout[lane]; const int32_t kp = ts->rg.dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
                 ts->dpos[lane] = pos + 2;
                 if (count_words) {
@@ -548,13 +549,13 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             if (lane < nd) ts->doff[lane] = A.b.off[r0 + lane];
             if (lane == 0) ts->doff[nd] = A.b.off[r0 + nd];
             __syncwarp();
-            walk_side<MODE>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+            walk_side<MODE, TokT>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         }
         // ---- closing </s>, row bookkeeping (one lane per row)
         if (lane < nd) {
             const int32_t pos = ts->dpos[lane];
             const int32_t dL = pos + 1;                                // framed length (>= W when the walk stopped early)
-            if (MODE == MODE_FIXED) { if (pos < limit) rowbufs[(size_t)lane * Wp + pos] = T.eos; }
+            if (MODE == MODE_FIXED) { if (pos < limit) rowbufs[(size_t)lane * Wp + pos] = (TokT)T.eos; }
             if (MODE == MODE_RAGGED) { if (pos < ts->rg.dkeep[lane]) A.ids[ts->rg.dout[lane] + pos] = T.eos; }
             const uint32_t fl = ts->dflag[lane];
             if (fl & F_DIRTY) {
@@ -599,12 +600,17 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 uint8_t* gm = A.mask ? A.mask + g0 : nullptr;
                 int8_t* gt = (A.has_pair && A.tt) ? A.tt + g0 : nullptr;
                 int8_t* gs = (A.has_pair && A.seq) ? A.seq + g0 : nullptr;
-                const int32_t* rb = rowbufs + i0;
+                const TokT* rb = rowbufs + i0;
                 for (int d = 0; d < nd; d++, gi += W, rb += Wp) {
                     const uint32_t em = ts->demit[d];
                     if (em & EM_SKIP) continue;
                     const int32_t c = (int32_t)(em & EM_LEN) - i0;      // real tokens from this quad on
-                    int4 v = *reinterpret_cast<const int4*>(rb);
+                    int4 v;
+                    if (sizeof(TokT) == 4) v = *reinterpret_cast<const int4*>(rb);
+                    else {
+                        const uint2 h = *reinterpret_cast<const uint2*>(rb);
+                        v = make_int4((int)(h.x & 0xFFFFu), (int)(h.x >> 16), (int)(h.y & 0xFFFFu), (int)(h.y >> 16));
+                    }
                     uint32_t mk;
                     if (!(em & EM_GENERIC)) {
                         v.x = c > 0 ? v.x : T.pad; v.y = c > 1 ? v.y : T.pad; v.z = c > 2 ? v.z : T.pad; v.w = c > 3 ? v.w : T.pad;
@@ -638,9 +644,9 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 const int64_t dr = r0 + d;
                 const int32_t Lr = (int32_t)(em & EM_LEN);
                 const bool trunc = (em & EM_TRUNC) != 0, generic_mask = (em & EM_GENERIC) != 0;
-                const int32_t* rb = rowbufs + (size_t)d * Wp;
+                const TokT* rb = rowbufs + (size_t)d * Wp;
                 for (int32_t i = lane; i < W; i += 32) {
-                    const int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : rb[i]) : T.pad;
+                    const int32_t t = i < Lr ? ((trunc && i == W - 1) ? T.eos : (int32_t)rb[i]) : T.pad;
                     A.ids[dr * W + i] = t;
                     if (generic_mask) tok_total += (uint32_t)(t != T.pad);
                     if (A.mask) A.mask[dr * W + i] = (uint8_t)(t != T.pad);

@@ -61,6 +61,7 @@ struct DeviceCtx {
     DevTables T{};
     WordCache C{};
     bool cache_ready = false;
+    bool force_wide = false;
     std::vector<void*> table_allocs;
     // chunk workspace
     DevBuf text, toff, pair, poff;                // inputs
@@ -85,6 +86,7 @@ struct genztok {
     int64_t max_chunk_bytes = 64ll << 20;
     int64_t chunk_rows = 1ll << 20;
     int64_t force_group = 0;
+    int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     std::vector<std::string> prof_names;
     std::map<std::string, std::pair<int64_t, double>> prof_acc;
     // pinned host pool
@@ -206,8 +208,15 @@ int ensure_cache(genztok_t* h, DeviceCtx* d) {
     return GENZTOK_OK;
 }
 
+// Rows are staged in shared memory as uint16 when every vocabulary id fits (the bundled model: 48,423 ids).
+bool narrow_ids(const DeviceCtx* d) { return !d->force_wide && d->T.n_ids <= 65536 && d->T.unk < 65536 && d->T.unk >= 0; }
+size_t row_stage_bytes(const DeviceCtx* d, int32_t W, int D) {
+    const size_t Wp = ((size_t)W + 3) & ~(size_t)3;
+    return ((size_t)D * Wp * (narrow_ids(d) ? 2 : 4) + 15) & ~(size_t)15;
+}
+
 // Documents per warp tile: aim at ~26 sixteen-byte pieces of text per window, bounded by the shared memory
-// the staged rows need (MODE_FIXED) so that at least two 8-warp blocks fit an SM.
+// the staged rows need (MODE_FIXED) so that four 8-warp blocks fit an SM when possible.
 int pick_tile_docs(genztok_t* h, const DeviceCtx* d, int64_t bytes_a, int64_t bytes_b, int64_t n, int32_t W, bool fixed) {
     int D;
     if (h->force_group) D = (int)h->force_group;
@@ -215,23 +224,19 @@ int pick_tile_docs(genztok_t* h, const DeviceCtx* d, int64_t bytes_a, int64_t by
         const int64_t avg = n > 0 ? std::max<int64_t>(std::max(bytes_a, bytes_b) / n, 1) : 1;
         D = (int)std::min<int64_t>(32, std::max<int64_t>(1, 416 / avg));
     }
-    if (fixed) {
-        const size_t row = (((size_t)W + 3) & ~(size_t)3) * 4;
-        while (D > 1 && 8 * (sizeof(TileSmem) + (size_t)D * row) > d->smem_optin / 2) D--;
-    }
+    if (fixed) while (D > 1 && 8 * (sizeof(TileSmem) + row_stage_bytes(d, W, D)) > d->smem_optin / 2) D--;
     return D;
 }
 
-template <int MODE>
-int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
+template <int MODE, typename TokT>
+int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
     const int D = A.row_list ? 1 : A.D;
-    const size_t row = (((size_t)A.W + 3) & ~(size_t)3) * 4;
-    auto smem_for = [&](int w) { return (size_t)w * (sizeof(TileSmem) + (MODE == MODE_FIXED ? (size_t)A.D * row : 0)); };
+    auto smem_for = [&](int w) { return (size_t)w * (sizeof(TileSmem) + (MODE == MODE_FIXED ? row_stage_bytes(d, A.W, A.D) : 0)); };
     int wpb = 8;
     while (wpb > 1 && smem_for(wpb) > d->smem_optin) wpb >>= 1;
     const size_t smem = smem_for(wpb);
     if (smem > d->smem_optin) return fail(h, GENZTOK_E_LIMIT, "row of %d ids does not fit shared memory", A.W);
-    auto kern = k_rows<MODE>;
+    auto kern = k_rows<MODE, TokT>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
@@ -244,9 +249,14 @@ int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, c
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
+template <int MODE>
+int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
+    if (MODE == MODE_FIXED && narrow_ids(d)) return launch_rows_t<MODE, uint16_t>(h, d, A, st, name, n_items_hint);
+    return launch_rows_t<MODE, int32_t>(h, d, A, st, name, n_items_hint);
+}
 
 // Can the fixed-layout kernel stage one row of W ids (one document per tile, one warp per block)?
-bool fixed_fits(const DeviceCtx* d, int32_t W) { return sizeof(TileSmem) + (((size_t)W + 3) & ~(size_t)3) * 4 <= d->smem_optin; }
+bool fixed_fits(const DeviceCtx* d, int32_t W) { return sizeof(TileSmem) + row_stage_bytes(d, W, 1) <= d->smem_optin; }
 
 int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force) {
     {
@@ -455,6 +465,9 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "group") {
         if (value < 0 || value > 32) return fail(h, GENZTOK_E_INVALID, "group (documents per warp tile) must be 0 (auto) or 1..32");
         h->force_group = value;
+    } else if (n == "wide_rows") {
+        h->force_wide = value;
+        for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
     } else return fail(h, GENZTOK_E_INVALID, "unknown option %s", n.c_str());
     return GENZTOK_OK;
 }

@@ -191,16 +191,58 @@ __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool la
     *len = last ? T.last_len[k] : T.mid_len[k];
 }
 
+static const int DEC_CAP = 2048;       // bytes staged per warp before a flush
+static const int DEC_MAXFORM = 32;     // forms longer than this go straight to global memory
+
+// Pass 1 (WRITE == false): bytes per row.  Pass 2: gather the forms into a per-warp shared-memory staging buffer
+// and write the text with aligned 16-byte stores (edges bytewise: neighbouring rows belong to other warps).
 template <bool WRITE>
 __global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t stage[WRITE ? 8 : 1][WRITE ? DEC_CAP + 16 : 16];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint8_t* ob = stage[WRITE ? wib : 0];
     for (uint64_t r = warp; r < (uint64_t)A.n_rows; r += nwarps) {
         const int64_t start = A.ids_off ? A.ids_off[r] : (int64_t)r * A.width;
         const int64_t n = A.ids_off ? A.ids_off[r + 1] - start : A.width;
         const int32_t* ids = A.ids + start;
-        int64_t run = 0;
-        uint8_t* dst = WRITE ? A.out + A.out_off[r] : nullptr;
+        if (!WRITE) {
+            int64_t run = 0;
+            for (int64_t base = 0; base < n; base += 32) {
+                const int64_t i = base + lane;
+                uint32_t off = 0, len = 0;
+                if (i < n) dec_form(T, ids[i], i == n - 1, &off, &len);
+                run += __reduce_add_sync(FULL_MASK, len);
+            }
+            if (lane == 0) A.out_len[r] = run;
+            continue;
+        }
+        const int64_t g0 = A.out_off[r];
+        uint8_t* gbase = A.out + (g0 & ~(int64_t)15);      // global address of ob[0]
+        int lead = (int)(g0 & 15);                          // ob[0..lead) is not ours (previous row)
+        int cur = lead;
+        // flush ob[0..upto) (upto multiple of 16, or everything when last): aligned 16-byte stores, foreign/partial units bytewise
+        auto flush = [&](int upto, bool last) {
+            __syncwarp();
+            const int nfull = last ? (cur & ~15) : upto;
+            for (int u = lane * 16; u < nfull; u += 512) {
+                if (u == 0 && lead) { for (int k = lead; k < 16; k++) gbase[k] = ob[k]; }
+                else *reinterpret_cast<uint4*>(gbase + u) = *reinterpret_cast<const uint4*>(ob + u);
+            }
+            if (last) {
+                const int rem = cur - nfull;                // trailing partial unit
+                if (lane < rem) { const int k = nfull + lane; if (!(nfull == 0 && k < lead)) gbase[k] = ob[k]; }
+                return;
+            }
+            __syncwarp();
+            const int rem = cur - nfull;
+            uint8_t keep = 0;
+            if (lane < rem) keep = ob[nfull + lane];
+            __syncwarp();
+            if (lane < rem) ob[lane] = keep;
+            gbase += nfull; cur = rem; lead = 0;
+            __syncwarp();
+        };
         for (int64_t base = 0; base < n; base += 32) {
             const int64_t i = base + lane;
             uint32_t off = 0, len = 0;
@@ -208,14 +250,31 @@ __global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
             uint32_t incl = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-            if (WRITE) {
-                uint8_t* d = dst + run + (incl - len);
-                const uint8_t* s = T.form_blob + off;
-                for (uint32_t k = 0; k < len; k++) d[k] = s[k];
+            const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+            const bool big = __any_sync(FULL_MASK, len > (uint32_t)DEC_MAXFORM);
+            const uint8_t* src = T.form_blob + off;
+            if (!big) {
+                if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
+                uint8_t* d = ob + cur + (incl - len);
+                for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+                cur += (int)tot;
+            } else {                                        // rare: a very long vocab entry -> write this batch directly
+                if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */
+                    __syncwarp();
+                    for (int k = lead + lane; k < cur; k += 32) gbase[k] = ob[k];
+                }
+                uint8_t* d = gbase + cur + (incl - len);
+                for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+                // restart the staging buffer at the new position
+                const int64_t gpos = (gbase - A.out) + cur + (int64_t)tot;
+                gbase = A.out + (gpos & ~(int64_t)15);
+                lead = (int)(gpos & 15);
+                cur = lead;
+                __syncwarp();
             }
-            run += __shfl_sync(FULL_MASK, incl, 31);
         }
-        if (!WRITE && lane == 0) A.out_len[r] = run;
+        flush(0, true);
+        __syncwarp();
     }
 }
 

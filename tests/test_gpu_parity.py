@@ -176,6 +176,7 @@ def test_every_tile_size_and_small_chunks(oracle, group):
     tok.set_option("max_chunk_bytes", 1 << 15)
     tok.set_option("chunk_rows", 257)
     tok.set_option("group", group)
+    tok.set_option("wide_rows", group % 2)      # odd tile sizes also exercise the int32 row staging
     for seed, paired, kw in [(201, True, dict(max_len=24)), (202, False, dict(max_len=64)), (203, True, dict())]:
         t = workload.generate(seed, 1500, 0, 20, 0.1)
         p = workload.generate(seed + 5000, 1500, 0, 20, 0.1) if paired else None
