@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgenztok.so")
+SO_PATH = os.environ.get("GENZTOK_LIB") or os.path.join(_HERE, "libgenztok.so")   # GENZTOK_LIB: try another build of the library
 
 MAX_LEN_NONE = -(2 ** 31)
 WANT_TOKEN_TYPE, WANT_SEQUENCE_ID, WANT_SPANS = 1, 2, 4
