@@ -59,7 +59,7 @@ struct RowArgs {
 static const int WIN_LANES = 30;            // pieces whose word starts a window handles; 2 more are look-ahead
 static const int WLIST_CAP = WIN_LANES * 8; // at most 8 word starts per 16-byte piece
 static const uint32_t F_DIRTY = 1u, F_SPECIAL = 2u, F_PADTOK = 4u;
-static const uint32_t EM_LEN = 0xFFFFFu, EM_TRUNC = 1u << 20, EM_GENERIC = 1u << 21, EM_SKIP = 1u << 22;
+static const uint32_t EM_LEN = 0xFFFFFu, EM_TRUNC = 1u << 20, EM_GENERIC = 1u << 21, EM_SKIP = 1u << 22, EM_SEQLONG = 1u << 23;
 
 // get_sequence_id + get_token_type in closed form for one row (see seq_describe)
 struct SeqDesc { int32_t p1, m, f1, f2, r1, r2, err; };
@@ -571,6 +571,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 if (A.has_pair) {
                     const SeqDesc sd = seq_describe(ts->dnA[lane], dL, W);
                     ts->dsd[lane] = sd;
+                    if (sd.m > Lr) ts->demit[lane] |= EM_SEQLONG;       // token types run on over the pads
                     if (A.seq_len) A.seq_len[dr] = sd.m;
                     if (A.status) A.status[dr] = (uint8_t)sd.err;
                     if ((fl & F_SPECIAL) || !T.specials_distinct) { const unsigned long long k = atomicAdd(&C.ctr[C_FIX], 1ULL); A.fix_list[k] = (uint32_t)dr; }
@@ -592,19 +593,21 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         if (MODE != MODE_FIXED) continue;
         // ---- FIXED: the warp writes its rows -----------------------------------------------------------
         if ((W & 15) == 0) {
-            // lane <-> quad column; rows of the tile in the inner loop so that everything but the row length is hoisted
-            for (int32_t i0 = lane * 4; i0 < W; i0 += 128) {
-                const bool lastq = i0 + 4 == W;
-                const size_t g0 = (size_t)r0 * (size_t)W + (size_t)i0;
-                int32_t* gi = A.ids + g0;
-                uint8_t* gm = A.mask ? A.mask + g0 : nullptr;
-                int8_t* gt = (A.has_pair && A.tt) ? A.tt + g0 : nullptr;
-                int8_t* gs = (A.has_pair && A.seq) ? A.seq + g0 : nullptr;
-                const TokT* rb = rowbufs + i0;
-                for (int d = 0; d < nd; d++, gi += W, rb += Wp) {
-                    const uint32_t em = ts->demit[d];
+            // Pass A: the quads that can hold real tokens (the first KQ of every row), 8 rows x 4 quads per step with
+            // the select logic.  Pass B: everything behind them is padding: constant 16-byte stores, one row per step.
+            uint32_t lr = 0;
+            if (lane < nd) { const uint32_t em = ts->demit[lane]; lr = (em & EM_SKIP) ? 0u : (em & EM_LEN); }
+            const int32_t KQ = (int32_t)(((__reduce_max_sync(FULL_MASK, lr) + 15u) >> 4) << 2);
+            const size_t grow = (size_t)r0 * (size_t)W;
+            for (int dg = 0; dg < nd; dg += 8) {
+                const int d = dg + (lane >> 2);
+                const uint32_t em = d < nd ? ts->demit[d] : EM_SKIP;
+                for (int32_t qb = 0; qb < KQ; qb += 4) {
+                    const int32_t i0 = (qb + (lane & 3)) * 4;
                     if (em & EM_SKIP) continue;
+                    const bool lastq = i0 + 4 == W;
                     const int32_t c = (int32_t)(em & EM_LEN) - i0;      // real tokens from this quad on
+                    const TokT* rb = rowbufs + (size_t)d * Wp + i0;
                     int4 v;
                     if (sizeof(TokT) == 4) v = *reinterpret_cast<const int4*>(rb);
                     else {
@@ -627,13 +630,35 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                         v = make_int4(x[0], x[1], x[2], x[3]);
                         tok_total += (uint32_t)__popc(mk);
                     }
-                    st_cs128(gi, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
-                    if (gm) st_cs32(gm + (size_t)d * W, mk);
-                    if (gt || gs) {
+                    const size_t g = grow + (size_t)d * W + i0;
+                    st_cs128(A.ids + g, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
+                    if (A.mask) st_cs32(A.mask + g, mk);
+                    if (A.has_pair && (A.tt || A.seq)) {
                         uint32_t ttw, sqw;
                         seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
-                        if (gt) st_cs32(gt + (size_t)d * W, ttw);
-                        if (gs) st_cs32(gs + (size_t)d * W, sqw);
+                        if (A.tt) st_cs32(A.tt + g, ttw);
+                        if (A.seq) st_cs32(A.seq + g, sqw);
+                    }
+                }
+            }
+            const int32_t qn = (W >> 2) - KQ;                           // pad-only quads per row
+            if (qn > 0) {
+                const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
+                const bool pairs_planes = A.has_pair && (A.tt || A.seq);
+                for (int d = 0; d < nd; d++) {
+                    const uint32_t em = ts->demit[d];
+                    if (em & EM_SKIP) continue;
+                    for (int32_t q = lane; q < qn; q += 32) {
+                        const int32_t i0 = (KQ + q) * 4;
+                        const size_t g = grow + (size_t)d * W + i0;
+                        st_cs128(A.ids + g, pad4);
+                        if (A.mask) st_cs32(A.mask + g, 0u);
+                        if (pairs_planes) {
+                            uint32_t ttw = 0u, sqw = 0xFEFEFEFEu;
+                            if (em & EM_SEQLONG) seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                            if (A.tt) st_cs32(A.tt + g, ttw);
+                            if (A.seq) st_cs32(A.seq + g, sqw);
+                        }
                     }
                 }
             }
