@@ -73,7 +73,7 @@ struct RaggedTile {            // MODE_COUNT / MODE_RAGGED only
     int32_t dwrd[32];          // words met so far in this side
 };
 struct __align__(16) TileSmem {
-    int64_t doff[33];          // document offsets of the tile for the side being walked
+    int32_t doff[34];          // document offsets of the tile for the side being walked, relative to the tile base (16-byte aligned)
     int32_t dpos[32];          // next token position per document
     int32_t dnA[32];           // tokens of side A per document
     uint32_t dflag[32];        // F_*
@@ -119,22 +119,23 @@ __device__ __forceinline__ uint32_t byte_of(const uint4& w, int j) {
 
 // Length (2 or 3) of the non-ASCII whitespace code point whose lead byte b0 sits at position p, else 0.
 // The 19 non-ASCII members of \s: C2 85, C2 A0, E1 9A 80, E2 80 80..8A, E2 80 A8/A9/AF, E2 81 9F, E3 80 80.
-__device__ __forceinline__ int multibyte_ws(uint32_t b0, const uint8_t* bytes, int64_t p, int64_t e) {
+// (positions are 32-bit offsets from the tile base `tb`)
+__device__ __forceinline__ int multibyte_ws(uint32_t b0, const uint8_t* tb, int32_t p, int32_t e) {
     if (b0 == 0xC2) {
-        if (p + 1 < e) { uint32_t b1 = bytes[p + 1]; if (b1 == 0x85 || b1 == 0xA0) return 2; }
+        if (p + 1 < e) { uint32_t b1 = tb[p + 1]; if (b1 == 0x85 || b1 == 0xA0) return 2; }
         return 0;
     }
     if (b0 < 0xE1 || b0 > 0xE3 || p + 2 >= e) return 0;
-    uint32_t b1 = bytes[p + 1];
-    if (b0 == 0xE1) return (b1 == 0x9A && bytes[p + 2] == 0x80) ? 3 : 0;
-    if (b0 == 0xE3) return (b1 == 0x80 && bytes[p + 2] == 0x80) ? 3 : 0;
-    if (b1 == 0x80) { uint32_t b2 = bytes[p + 2]; return ((b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF) ? 3 : 0; }
-    if (b1 == 0x81) return bytes[p + 2] == 0x9F ? 3 : 0;
+    uint32_t b1 = tb[p + 1];
+    if (b0 == 0xE1) return (b1 == 0x9A && tb[p + 2] == 0x80) ? 3 : 0;
+    if (b0 == 0xE3) return (b1 == 0x80 && tb[p + 2] == 0x80) ? 3 : 0;
+    if (b1 == 0x80) { uint32_t b2 = tb[p + 2]; return ((b2 >= 0x80 && b2 <= 0x8A) || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF) ? 3 : 0; }
+    if (b1 == 0x81) return tb[p + 2] == 0x9F ? 3 : 0;
     return 0;
 }
 
 // index of the document that holds byte position p: largest k in [0, nd) with doff[k] <= p
-__device__ __forceinline__ int doc_of(const int64_t* doff, int nd, int64_t p) {
+__device__ __forceinline__ int doc_of(const int32_t* doff, int nd, int32_t p) {
     int lo = 0, hi = nd - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -145,10 +146,10 @@ __device__ __forceinline__ int doc_of(const int64_t* doff, int nd, int64_t p) {
 
 // Whitespace bits of the 16 bytes at `a` (bits 0..15) plus spill into the next piece (bits 16,17).
 // Bytes outside [S,E) count as whitespace; a multi-byte whitespace never straddles two documents.
-__device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* bytes, int64_t a, int64_t S, int64_t E, const int64_t* doff, int nd) {
+__device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* tb, int32_t a, int32_t S, int32_t E, const int32_t* doff, int nd) {
     uint32_t inseg = 0xFFFFu;
-    if (a < S) inseg &= 0xFFFFu << (int)(S - a);
-    if (a + 16 > E) inseg &= 0xFFFFu >> (int)(a + 16 - E);
+    if (a < S) inseg &= 0xFFFFu << (S - a);
+    if (a + 16 > E) inseg &= 0xFFFFu >> (a + 16 - E);
     uint32_t ws = gather_msb(ascii_ws4(w.x)) | (gather_msb(ascii_ws4(w.y)) << 4) | (gather_msb(ascii_ws4(w.z)) << 8) |
                   (gather_msb(ascii_ws4(w.w)) << 12);
     if ((w.x | w.y | w.z | w.w) & 0x80808080u) {
@@ -161,7 +162,7 @@ __device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* by
             while (lead) {
                 const int j = __ffs(lead) - 1;
                 lead &= lead - 1;
-                const int l = multibyte_ws(byte_of(w, j), bytes, a + j, E);
+                const int l = multibyte_ws(byte_of(w, j), tb, a + j, E);
                 if (l && a + j + l <= doff[doc_of(doff, nd, a + j) + 1]) ws |= ((1u << l) - 1) << j;
             }
         }
@@ -170,11 +171,11 @@ __device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* by
 }
 
 // First whitespace position at or after q (q is on a code point boundary or inside a non-ws one).
-__device__ __noinline__ int64_t slow_word_end(const uint8_t* bytes, int64_t q, int64_t e) {
+__device__ __noinline__ int32_t slow_word_end(const uint8_t* tb, int32_t q, int32_t e) {
     while (q < e) {
-        uint32_t b = bytes[q];
+        uint32_t b = tb[q];
         if (b <= 0x20) { if ((b >= 0x09 && b <= 0x0D) || b >= 0x1C) return q; }
-        else if (b >= 0xC2 && multibyte_ws(b, bytes, q, e)) return q;
+        else if (b >= 0xC2 && multibyte_ws(b, tb, q, e)) return q;
         q++;
     }
     return e;
@@ -182,9 +183,10 @@ __device__ __noinline__ int64_t slow_word_end(const uint8_t* bytes, int64_t q, i
 
 // ---- word -> cache slot --------------------------------------------------------------------------
 // 24-byte zero-padded key of the word at [p, p+len), len <= 24, via aligned 16-byte loads.
-__device__ __forceinline__ void load_key24(const uint8_t* bytes, int64_t p, uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
-    const int64_t A = p & ~(int64_t)15;
-    int sh = (int)(p - A);
+__device__ __forceinline__ void load_key24(const uint8_t* tb, int32_t p, uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    const int32_t A = p & ~15;
+    int sh = p & 15;
+    const uint8_t* bytes = tb;
     const int need = sh + (int)len;
     uint4 v0 = ldg128(bytes + A);
     uint64_t q0 = ((uint64_t)v0.y << 32) | v0.x, q1 = ((uint64_t)v0.w << 32) | v0.z, q2 = 0, q3 = 0, q4 = 0;
@@ -198,6 +200,24 @@ __device__ __forceinline__ void load_key24(const uint8_t* bytes, int64_t p, uint
         }
     }
     if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; sh -= 8; }
+    uint64_t r0 = q0, r1 = q1, r2 = q2;
+    if (sh) {
+        const int s8 = sh * 8;
+        r0 = (q0 >> s8) | (q1 << (64 - s8));
+        r1 = (q1 >> s8) | (q2 << (64 - s8));
+        r2 = (q2 >> s8) | (q3 << (64 - s8));
+    }
+    if (len <= 8) { if (len < 8) r0 &= (1ULL << (len * 8)) - 1; r1 = 0; r2 = 0; }
+    else if (len <= 16) { if (len < 16) r1 &= (1ULL << ((len - 8) * 8)) - 1; r2 = 0; }
+    else if (len < 24) r2 &= (1ULL << ((len - 16) * 8)) - 1;
+    *k0 = r0; *k1 = r1; *k2 = r2;
+}
+
+// The same key from two 16-byte pieces already in registers (word inside 32 bytes from its aligned start): lets the
+// caller issue the piece loads before the word length is final.
+__device__ __forceinline__ void key_from_pieces(const uint4& v0, const uint4& v1, int sh, uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    uint64_t q0 = ((uint64_t)v0.y << 32) | v0.x, q1 = ((uint64_t)v0.w << 32) | v0.z, q2 = ((uint64_t)v1.y << 32) | v1.x, q3 = ((uint64_t)v1.w << 32) | v1.z;
+    if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; q3 = 0; sh -= 8; }
     uint64_t r0 = q0, r1 = q1, r2 = q2;
     if (sh) {
         const int s8 = sh * 8;
@@ -260,6 +280,28 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
     }
 }
 
+// One probe of the word's home slot with ordinary (L1-cacheable) loads: the common case of a word already in the
+// cache.  Returns false when the slot does not hold this word (then lookup_slow decides).
+__device__ __forceinline__ bool cache_probe_fast(const WordCache& C, uint32_t len, uint64_t k0, uint64_t k1, uint64_t k2, uint32_t h, uint32_t* val) {
+    const uint4* s = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
+    const uint4 a = s[0], b = s[1];
+    const uint64_t s0 = ((uint64_t)a.w << 32) | a.z, s1 = ((uint64_t)b.y << 32) | b.x, s2 = ((uint64_t)b.w << 32) | b.z;
+    *val = a.y;
+    return (a.x == len) & (s0 == k0) & (s1 == k1) & (s2 == k2);
+}
+
+// Everything that is not the fast path: words whose end is not known from the window registers, long keys,
+// probe chains, insertion.  Recomputes the word end from the bytes.  Out of line on purpose.
+__device__ __noinline__ uint32_t lookup_slow(const WordCache& C, const uint8_t* tb, int32_t p, int32_t e_doc, int insert_ok) {
+    int32_t end = slow_word_end(tb, p + 1, e_doc);
+    if (end < e_doc && tb[end] == 0x0A) end++;                         // \S+\n?  (tokenize.py:106)
+    const uint32_t len = (uint32_t)(end - p);
+    uint64_t k0, k1, k2; uint32_t h;
+    if (len <= KEY_INLINE) { load_key24(tb, p, len, &k0, &k1, &k2); h = hash_key24(k0, k1, k2, len); }
+    else { k1 = hash_long(tb + p, len); k0 = 0; k2 = 0; h = fmix32((uint32_t)k1 ^ (uint32_t)(k1 >> 32)); }
+    return cache_find_or_insert(C, tb + p, len, k0, k1, k2, h, insert_ok != 0);
+}
+
 // ---- token types for a pair row in closed form ---------------------------------------------------
 // get_sequence_id + get_token_type (tokenize.py:154-182) evaluated on the known positions of
 // </s> in a row without interior special ids.  Generic rows go to k_post_rows.
@@ -320,53 +362,54 @@ __device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t
 }
 
 // ---- walking one side of a tile --------------------------------------------------------------------
-// All 32 lanes call this.  ts->doff[0..nd] holds the side's document offsets, ts->dpos[] the next token
-// position of every row.  Tokens at positions < limit are delivered to rowbufs (FIXED) / ts->dout (RAGGED).
+// All 32 lanes call this.  ts->doff[0..nd] holds the side's document offsets relative to the tile base `tb`
+// (16-byte aligned), ts->dpos[] the next token position of every row.  Tokens at positions < limit are delivered to
+// rowbufs (FIXED) / ts->rg.dout (RAGGED).  All byte positions are 32-bit offsets from tb.
 template <int MODE, typename TokT>
-__device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ bytes, TileSmem* ts, int nd,
+__device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ tb, TileSmem* ts, int nd,
                                           int lane, int32_t limit, TokT* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
-    const int64_t S = ts->doff[0], E = ts->doff[nd];
+    const int32_t S = ts->doff[0], E = ts->doff[nd];
+    if (E <= S) return;
     // documents that are empty share their start with the next one: then the per-piece start bits cannot number
     // documents and every word finds its document by binary search instead
     const bool has_empty = __any_sync(FULL_MASK, lane < nd && ts->doff[lane + 1] == ts->doff[lane]);
+    const int32_t spec_max = max(T.pad, max(T.bos, T.eos));
     int dbase = 0;                // documents that started before the current window
-    if (E <= S) return;
-    const int64_t base = S & ~(int64_t)15;
-    const int32_t n_win = (int32_t)((E - base + 16 * WIN_LANES - 1) / (16 * WIN_LANES));
+    const int32_t n_win = (E + 16 * WIN_LANES - 1) / (16 * WIN_LANES);
     uint32_t carry = 1u << 15;    // the byte before the tile is whitespace, nothing spills in
     for (int32_t w = 0; w < n_win; ++w) {
-        const int64_t wbase = base + (int64_t)w * (16 * WIN_LANES);
-        const int64_t a = wbase + lane * 16;
+        const int32_t wbase = w * (16 * WIN_LANES);
+        const int32_t a = wbase + lane * 16;
         // document starts inside this window -> bits per piece
         ts->bnd[lane] = 0;
         __syncwarp();
         if (lane + 1 < nd) {
-            const int64_t o = ts->doff[lane + 1] - wbase;
-            if (o >= 0 && o < 16 * 32) atomicOr(&ts->bnd[o >> 4], 1u << (o & 15));
+            const uint32_t o = (uint32_t)(ts->doff[lane + 1] - wbase);
+            if (o < 16u * 32u) atomicOr(&ts->bnd[o >> 4], 1u << (o & 15));
         }
         __syncwarp();
         uint32_t ws18 = 0xFFFFu;
         if (a < E) {
-            const uint4 v = ldg128(bytes + a);
-            ws18 = classify16(v, bytes, a, S, E, ts->doff, nd);
+            const uint4 v = ldg128(tb + a);
+            ws18 = classify16(v, tb, a, S, E, ts->doff, nd);
         }
         uint32_t prev = __shfl_up_sync(FULL_MASK, ws18, 1);
         if (lane == 0) prev = carry;
         carry = __shfl_sync(FULL_MASK, ws18, WIN_LANES - 1);
         const uint32_t nw = ~(ws18 | (prev >> 16)) & 0xFFFFu;
-        uint32_t st = nw & (~((nw << 1) | ((~prev >> 15) & 1u)) | ts->bnd[lane]);
+        const uint32_t b16 = ts->bnd[lane];
+        uint32_t st = nw & (~((nw << 1) | ((~prev >> 15) & 1u)) | b16);
         if (lane >= WIN_LANES) st = 0;                      // look-ahead pieces: their words belong to the next window
         // non-whitespace bits of the following pieces: word ends without touching memory
-        uint64_t win = nw;
+        uint32_t win_lo = nw, win_hi = 0;
         {
             const uint32_t n1 = __shfl_down_sync(FULL_MASK, nw, 1), n2 = __shfl_down_sync(FULL_MASK, nw, 2), n3 = __shfl_down_sync(FULL_MASK, nw, 3);
-            if (lane + 1 < 32) win |= (uint64_t)n1 << 16;
-            if (lane + 2 < 32) win |= (uint64_t)n2 << 32;
-            if (lane + 3 < 32) win |= (uint64_t)n3 << 48;
+            if (lane + 1 < 32) win_lo |= n1 << 16;
+            if (lane + 2 < 32) win_hi = n2;
+            if (lane + 3 < 32) win_hi |= n3 << 16;
         }
         const int known = 16 * ((32 - lane) < 4 ? (32 - lane) : 4);
         // ---- compact my word starts into the word list (and number the documents by counting start bits)
-        const uint32_t b16 = ts->bnd[lane];
         const int cnt = __popc(st);
         int incl = cnt | (__popc(b16) << 16);
 #pragma unroll
@@ -378,8 +421,11 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
         while (st) {
             const int b = __ffs(st) - 1;
             st &= st - 1;
-            const uint64_t z = (~win) >> (b + 1);
-            int run = z ? __ffsll((long long)z) : 65;       // bytes from the word start to the first whitespace
+            // bytes from the word start to the first whitespace: first zero of the window above bit b
+            const uint32_t zl = ~__funnelshift_r(win_lo, win_hi, b + 1);   // window bits b+1 .. b+32
+            int run;
+            if (zl) run = __ffs(zl);
+            else { const uint32_t zh = ~(win_hi >> (b + 1)); run = 32 + __ffs(zh); }   // zh != 0: the shift brings in zeros
             if (b + run >= known) run = 0;                  // not decided inside the window registers
             const int doc = dlane + __popc(b16 & ((2u << b) - 1));
             ts->wlist[k++] = (uint32_t)((lane * 16 + b) | (run << 9) | (doc << 16));
@@ -392,39 +438,58 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             int doc = 0x7FFF;
             uint32_t nt = 0, val = 0;
             bool pending = false;
-            int64_t p = 0;
-            uint32_t wl = 0;
             if (has) {
-                wl = ts->wlist[j];
-                p = wbase + (wl & 511u);
+                const uint32_t wl = ts->wlist[j];
+                const int32_t p = wbase + (int32_t)(wl & 511u);
                 doc = has_empty ? doc_of(ts->doff, nd, p) : (int)(wl >> 16);
+                // a word of a row that is already full cannot matter (and need not be known): skip its lookup
+                if (ts->dpos[doc] < limit) {
+                    const int32_t run = (int32_t)((wl >> 9) & 127u);
+                    const int32_t e_doc = ts->doff[doc + 1];
+                    const int32_t end0 = min(p + run, e_doc);
+                    // issue every load the fast path needs at once: the byte behind the word (\S+\n?, tokenize.py:106)
+                    // and the one or two aligned pieces that hold the word and that byte
+                    const int sh = p & 15;
+                    const int32_t span = sh + (end0 - p) + 1;
+                    const bool fast = run != 0 && (end0 - p) < (int32_t)KEY_INLINE && span <= 32;
+                    uint32_t nlb = 0;
+                    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+                    if (end0 < e_doc) nlb = tb[end0];
+                    if (fast) {
+                        v0 = ldg128(tb + (p & ~15));
+                        if (span > 16) v1 = ldg128(tb + (p & ~15) + 16);
+                    }
+                    const uint32_t len = (uint32_t)(end0 - p) + (nlb == 0x0A ? 1u : 0u);
+                    bool hit = false;
+                    if (fast) {
+                        uint64_t k0, k1, k2;
+                        key_from_pieces(v0, v1, sh, len, &k0, &k1, &k2);
+                        hit = cache_probe_fast(C, len, k0, k1, k2, hash_key24(k0, k1, k2, len), &val);
+                    }
+                    if (!hit) val = lookup_slow(C, tb, p, e_doc, insert_ok ? 1 : 0);
+                    const uint32_t kind = val & VAL_KIND;
+                    if (kind == VAL_SINGLE) nt = 1;
+                    else if (kind == VAL_MULTI) nt = C.tok_arena[val & VAL_PAYLOAD];
+                    else pending = true;                                // BPE not run yet (counts as 0 tokens for now)
+                }
             }
-            // a word of a row that is already full cannot matter (and need not be known): skip its lookup
-            if (has && ts->dpos[doc] < limit) {
-                const int run = (int)((wl >> 9) & 127u);
-                const int64_t e_doc = ts->doff[doc + 1];
-                int64_t end = run ? p + run : slow_word_end(bytes, p + 1, e_doc);
-                if (end > e_doc) end = e_doc;
-                if (end < e_doc && bytes[end] == 0x0A) end++;          // \S+\n?  (tokenize.py:106)
-                const uint32_t len = (uint32_t)(end - p);
-                uint64_t k0, k1, k2; uint32_t h;
-                if (len <= KEY_INLINE) { load_key24(bytes, p, len, &k0, &k1, &k2); h = hash_key24(k0, k1, k2, len); }
-                else { k1 = hash_long(bytes + p, len); k0 = 0; k2 = 0; h = fmix32((uint32_t)k1 ^ (uint32_t)(k1 >> 32)); }
-                val = cache_find_or_insert(C, bytes + p, len, k0, k1, k2, h, insert_ok);
-                const uint32_t kind = val & VAL_KIND;
-                if (kind == VAL_SINGLE) nt = 1;
-                else if (kind == VAL_MULTI) nt = C.tok_arena[val & VAL_PAYLOAD];
-                else pending = true;                                   // BPE not run yet (counts as 0 tokens for now)
-            }
-            // position of my first token: segmented inclusive scan of nt over equal doc
-            uint32_t sc = nt;
+            // position of my first token: inclusive count of nt over the lanes of my document up to me
+            const int dprev = __shfl_up_sync(FULL_MASK, doc, 1);
+            const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0 || dprev != doc);
+            const int seg0 = 31 - __clz(heads & ((2u << lane) - 1));   // first lane of my document in this batch
+            uint32_t sc;
+            if (__all_sync(FULL_MASK, nt <= 1)) {                        // the usual case: every word is one token
+                const uint32_t ones = __ballot_sync(FULL_MASK, nt == 1);
+                sc = __popc(ones & ((2u << lane) - 1) & ~((1u << seg0) - 1));
+            } else {
+                sc = nt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o);
-                const int dsrc = __shfl_up_sync(FULL_MASK, doc, o);
-                if (lane >= o && dsrc == doc) sc += t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o);
+                    if (lane - o >= seg0) sc += t;
+                }
             }
-            const int dnext = __shfl_down_sync(FULL_MASK, doc, 1);
+            const bool seg_last = lane == 31 || ((heads >> (lane + 1)) & 1u);
             int32_t q = 0;
             if (has) q = ts->dpos[doc] + (int32_t)(sc - nt);
             // q is a lower bound of the word's position while earlier words are pending: if even that is past the
@@ -432,13 +497,11 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             if (pending && q < limit) atomicOr(&ts->dflag[doc], F_DIRTY);
             int wrank = 0, wbase_idx = 0;
             if (MODE != MODE_FIXED && count_words) {                     // word index inside the row (return_offset)
-                const int dprev = __shfl_up_sync(FULL_MASK, doc, 1);
-                const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0 || dprev != doc);
-                wrank = lane - (31 - __clz(heads & ((2u << lane) - 1)));
+                wrank = lane - seg0;
                 if (has) wbase_idx = ts->rg.dwrd[doc];
             }
             __syncwarp();
-            if (has && (lane == 31 || dnext != doc)) {
+            if (has && seg_last) {
                 ts->dpos[doc] = q + (int32_t)nt;
                 if (MODE != MODE_FIXED && count_words) ts->rg.dwrd[doc] = wbase_idx + wrank + 1;
             }
@@ -454,15 +517,13 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                 uint32_t fl = 0;
                 if (nt == 1) {
                     const int32_t t = (int32_t)(val & VAL_PAYLOAD);
-                    if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
-                    if (t == T.pad) fl |= F_PADTOK;
+                    if (t <= spec_max) { if (t == T.eos || t == T.bos) fl |= F_SPECIAL; if (t == T.pad) fl |= F_PADTOK; }
                     if (q < lim) { if (MODE == MODE_FIXED) dsts[q] = (TokT)t; else dstg[q] = t; }
                 } else {
                     const uint32_t* src = C.tok_arena + (val & VAL_PAYLOAD) + 1;
                     for (uint32_t i = 0; i < nt && q < lim; i++, q++) {
                         const int32_t t = (int32_t)src[i];
-                        if (t == T.eos || t == T.bos) fl |= F_SPECIAL;
-                        if (t == T.pad) fl |= F_PADTOK;
+                        if (t <= spec_max) { if (t == T.eos || t == T.bos) fl |= F_SPECIAL; if (t == T.pad) fl |= F_PADTOK; }
                         if (MODE == MODE_FIXED) dsts[q] = (TokT)t; else dstg[q] = t;
                     }
                 }
@@ -502,8 +563,12 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         const uint32_t left = n_items - tile * Dt;
         const int nd = (int)(Dt < left ? Dt : left);
         // ---- set up the tile
-        if (lane < nd) ts->doff[lane] = A.a.off[r0 + lane];
-        if (lane == 0) ts->doff[nd] = A.a.off[r0 + nd];            // nd may be 32: 33 offsets
+        // document offsets relative to the 16-byte aligned start of the tile's text (nd may be 32: 33 offsets)
+        int64_t o64 = lane <= nd ? A.a.off[r0 + lane] : 0;
+        const int64_t o32nd = nd == 32 ? A.a.off[r0 + 32] : 0;
+        int64_t tbase = __shfl_sync(FULL_MASK, o64, 0) & ~(int64_t)15;
+        if (lane <= nd) ts->doff[lane] = (int32_t)(o64 - tbase);
+        if (nd == 32 && lane == 0) ts->doff[32] = (int32_t)(o32nd - tbase);
         const bool count_words = MODE != MODE_FIXED && ((MODE == MODE_COUNT && A.nwA) || (MODE == MODE_RAGGED && A.spans));
         if (lane < nd) {
             ts->dpos[lane] = 1;                                    // position 0 is <s> (tokenize.py:135)
@@ -519,7 +584,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             }
         }
         __syncwarp();
-        walk_side<MODE, TokT>(T, C, A.a.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+        walk_side<MODE, TokT>(T, C, A.a.bytes + tbase, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         if (A.has_pair) {
             // ... </s> </s> B   (tokenize.py:237-239)
             if (lane < nd) {
@@ -546,10 +611,13 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 }
             }
             __syncwarp();
-            if (lane < nd) ts->doff[lane] = A.b.off[r0 + lane];
-            if (lane == 0) ts->doff[nd] = A.b.off[r0 + nd];
+            o64 = lane <= nd ? A.b.off[r0 + lane] : 0;
+            const int64_t p32nd = nd == 32 ? A.b.off[r0 + 32] : 0;
+            tbase = __shfl_sync(FULL_MASK, o64, 0) & ~(int64_t)15;
+            if (lane <= nd) ts->doff[lane] = (int32_t)(o64 - tbase);
+            if (nd == 32 && lane == 0) ts->doff[32] = (int32_t)(p32nd - tbase);
             __syncwarp();
-            walk_side<MODE, TokT>(T, C, A.b.bytes, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+            walk_side<MODE, TokT>(T, C, A.b.bytes + tbase, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         }
         // ---- closing </s>, row bookkeeping (one lane per row)
         if (lane < nd) {
