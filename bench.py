@@ -180,6 +180,9 @@ def main():
     tb, to = workload.generate(SEED, n, 3, 13, 0.0, first_chunk=rank)
     in_bytes = int(to[-1])
     tok = Tokenize(devices=[local_rank])
+    for kv in os.environ.get("GENZTOK_OPTIONS", "").split(","):      # e.g. GENZTOK_OPTIONS=grid_mult=4,group=7 (experiments)
+        if "=" in kv:
+            tok.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     # ---- device-resident leg ---------------------------------------------------------------------
     pad = (-in_bytes) % 16 + 16

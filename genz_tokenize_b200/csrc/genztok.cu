@@ -21,6 +21,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/genztok.h"
@@ -82,11 +83,13 @@ struct genztok {
     std::string err;
     std::atomic<int64_t> launches{0};
     std::mutex mu;                       // encode/decode calls are serialised per handle
+    std::mutex err_mu;                   // guards err / prof_names (device worker threads)
     // options
     int64_t max_chunk_bytes = 64ll << 20;
     int64_t chunk_rows = 1ll << 20;
     int64_t force_group = 0;
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
+    int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
     std::vector<std::string> prof_names;
     std::map<std::string, std::pair<int64_t, double>> prof_acc;
     // pinned host pool
@@ -102,7 +105,7 @@ int fail(genztok_t* h, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (h) h->err = buf; else g_create_err = buf;
+    if (h) { std::lock_guard<std::mutex> l(h->err_mu); h->err = buf; } else g_create_err = buf;
     return code;
 }
 
@@ -113,6 +116,7 @@ int fail(genztok_t* h, int code, const char* fmt, ...) {
     } while (0)
 
 int prof_name_id(genztok_t* h, const char* name) {
+    std::lock_guard<std::mutex> l(h->err_mu);
     for (size_t i = 0; i < h->prof_names.size(); i++) if (h->prof_names[i] == name) return (int)i;
     h->prof_names.push_back(name);
     return (int)h->prof_names.size() - 1;
@@ -242,7 +246,7 @@ int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st,
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
     if (occ < 1) occ = 1;
     const int64_t tiles = (n_items_hint + D - 1) / D;
-    int64_t blocks = std::min<int64_t>((tiles + wpb - 1) / wpb, (int64_t)d->sm_count * occ);
+    int64_t blocks = std::min<int64_t>((tiles + wpb - 1) / wpb, (int64_t)d->sm_count * occ * h->grid_mult);
     if (blocks < 1) blocks = 1;
     LaunchScope ls(h, d, name);
     kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(d->T, d->C, A);
@@ -465,6 +469,9 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "group") {
         if (value < 0 || value > 32) return fail(h, GENZTOK_E_INVALID, "group (documents per warp tile) must be 0 (auto) or 1..32");
         h->force_group = value;
+    } else if (n == "grid_mult") {
+        if (value < 1 || value > 1024) return fail(h, GENZTOK_E_INVALID, "grid_mult must be in 1..1024");
+        h->grid_mult = value;
     } else if (n == "wide_rows") {
         h->force_wide = value;
         for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
@@ -552,105 +559,74 @@ void genztok_free_encoded(genztok_t* h, genztok_encoded_t* out) {
     memset(out, 0, sizeof *out);
 }
 
-int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, const uint8_t* pair, const int64_t* pair_off, int64_t n,
-                   int32_t max_len, int padding, int truncation, uint32_t flags, genztok_encoded_t* out) {
-    if (!h) return GENZTOK_E_INVALID;
-    if (!out || n < 0 || !text_off) return fail(h, GENZTOK_E_INVALID, "genztok_encode: bad arguments");
-    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
-    memset(out, 0, sizeof *out);
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceCtx* d = h->devs[0];
-    CU(cudaSetDevice(d->device));
+}  // extern "C"
+
+namespace {
+
+// Everything one device does for its contiguous range of rows [rb, re): chunk loop, H2D, kernels, D2H.
+// Fixed layout: results land in the caller-visible pinned planes of `out` at the rows' final places.
+// Ragged layout: flat planes are collected in `part` (offsets relative to the part) and stitched by the caller.
+struct EncodeJob {
+    const uint8_t* text; const int64_t* text_off; const uint8_t* pair; const int64_t* pair_off;
+    int32_t max_len; int padding, truncation; uint32_t flags;
+    bool has_pair, has_max_len, want_spans, fixed, want_tt, want_seq;
+    genztok_encoded_t* out;
+};
+struct EncodePart {
+    int rc = GENZTOK_OK;
+    std::string err;
+    std::vector<int32_t> ids, spans; std::vector<uint8_t> mask; std::vector<int8_t> tt, seq;
+    int64_t total = 0, span_total = 0, tokens = 0;
+};
+
+void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64_t rb, int64_t re, EncodePart* part) {
+    genztok_encoded_t* out = J.out;
+    const bool has_pair = J.has_pair, has_max_len = J.has_max_len, want_spans = J.want_spans, fixed = J.fixed, want_tt = J.want_tt, want_seq = J.want_seq;
+    const int32_t max_len = J.max_len;
     cudaStream_t st = d->stream;
+#define PFAIL(code, ...) { char _b[400]; snprintf(_b, sizeof _b, __VA_ARGS__); part->rc = (code); part->err = _b; cudaStreamSynchronize(st); return; }
+#define FAIL_RC(call) { int _rc = (call); if (_rc) { part->rc = _rc; { std::lock_guard<std::mutex> _l(h->err_mu); part->err = h->err; } cudaStreamSynchronize(st); return; } }
+#define CUF(call) { cudaError_t _e = (call); if (_e != cudaSuccess) PFAIL(GENZTOK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__) }
+    CUF(cudaSetDevice(d->device));
     LaunchScope::cur_stream = st;
-    const bool has_pair = pair_off != nullptr;
-    const bool has_max_len = max_len != GENZTOK_MAX_LEN_NONE;
-    const bool want_spans = (flags & GENZTOK_WANT_SPANS) != 0;       // return_offset: produced by the ragged pipeline
-    const bool fixed = has_max_len && max_len >= 1 && padding && truncation && fixed_fits(d, max_len) && !want_spans;
     const int8_t eos8 = eos_as_i8(d);
-    OutBlock* ob = new OutBlock();
-    out->_owner = ob;
-    out->n = n; out->has_pair = has_pair;
-    const bool want_tt = has_pair && (flags & GENZTOK_WANT_TOKEN_TYPE), want_seq = has_pair && (flags & GENZTOK_WANT_SEQUENCE_ID);
-
-#define OOM_CHECK(p) if (!(p)) { genztok_free_encoded_nolock(h, out); return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
-    auto genztok_free_encoded_nolock = [](genztok_t* hh, genztok_encoded_t* o) {
-        OutBlock* b = reinterpret_cast<OutBlock*>(o->_owner);
-        for (auto& pr : b->pinned) { hh->host_pool.insert({pr.second, pr.first}); hh->host_pool_bytes += pr.second; }
-        for (void* p : b->mallocs) free(p);
-        delete b;
-        memset(o, 0, sizeof *o);
-    };
-#define FAIL_RC(rc) { int _rc = (rc); if (_rc) { cudaStreamSynchronize(st); genztok_free_encoded_nolock(h, out); return _rc; } }
-#define CUF(call) { cudaError_t _e = (call); if (_e != cudaSuccess) { cudaStreamSynchronize(st); genztok_free_encoded_nolock(h, out); \
-        return fail(h, GENZTOK_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); } }
-
     // chunk boundaries: rows [r0, r1) with at most chunk_rows rows and max_chunk_bytes bytes
-    std::vector<int64_t> cuts{0};
+    std::vector<int64_t> cuts{rb};
     {
-        int64_t r0 = 0;
-        while (r0 < n) {
-            int64_t r1 = std::min<int64_t>(n, r0 + h->chunk_rows);
-            auto bytes_of = [&](int64_t a, int64_t b) { return (text_off[b] - text_off[a]) + (has_pair ? pair_off[b] - pair_off[a] : 0) + 64; };
+        int64_t r0 = rb;
+        while (r0 < re) {
+            int64_t r1 = std::min<int64_t>(re, r0 + h->chunk_rows);
+            auto bytes_of = [&](int64_t a, int64_t b) { return (J.text_off[b] - J.text_off[a]) + (has_pair ? J.pair_off[b] - J.pair_off[a] : 0) + 64; };
             if (bytes_of(r0, r1) > h->max_chunk_bytes) {
                 int64_t lo = r0 + 1, hi = r1;   // largest r1 that fits (at least one row)
                 while (lo < hi) { int64_t mid = (lo + hi + 1) / 2; if (bytes_of(r0, mid) <= h->max_chunk_bytes) lo = mid; else hi = mid - 1; }
                 r1 = lo;
-                if (bytes_of(r0, r1) > h->max_chunk_bytes) {
-                    genztok_free_encoded_nolock(h, out);
-                    return fail(h, GENZTOK_E_LIMIT, "document %lld is larger than max_chunk_bytes=%lld", (long long)r0, (long long)h->max_chunk_bytes);
-                }
+                if (bytes_of(r0, r1) > h->max_chunk_bytes)
+                    PFAIL(GENZTOK_E_LIMIT, "document %lld is larger than max_chunk_bytes=%lld", (long long)r0, (long long)h->max_chunk_bytes)
             }
             cuts.push_back(r1);
             r0 = r1;
         }
     }
     FAIL_RC(ensure_cache(h, d));
-
-    // ragged accumulators (host, pageable)
-    std::vector<int32_t> r_ids; std::vector<uint8_t> r_mask; std::vector<int8_t> r_tt, r_seq;
-    std::vector<int32_t> r_spans;
-    if (want_spans) { out->span_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->span_off); out->span_off[0] = 0; }
-    int64_t span_total = 0;
-    if (fixed) {
-        const size_t tot = (size_t)n * (size_t)max_len;
-        out->width = max_len; out->total = (int64_t)tot;
-        out->input_ids = out_alloc<int32_t>(h, ob, tot); OOM_CHECK(out->input_ids);
-        out->attention_mask = out_alloc<uint8_t>(h, ob, tot); OOM_CHECK(out->attention_mask);
-        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
-        if (want_tt) { out->token_type_ids = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->token_type_ids); out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len); }
-        if (want_seq) { out->sequence_id = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->sequence_id); }
-        if (has_pair) { out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len); out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status); }
-    } else {
-        out->width = 0;
-        out->row_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->row_off);
-        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
-        if (has_pair) {
-            out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len);
-            out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len);
-            out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status);
-        }
-        out->row_off[0] = 0;
-    }
     unsigned long long tokens_before = 0;
     CUF(cudaMemcpyAsync(&tokens_before, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaStreamSynchronize(st));
 
-    int64_t ragged_total = 0;
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], m = r1 - r0;
-        const int64_t tb0 = text_off[r0], tb = text_off[r1] - tb0;
-        const int64_t pb0 = has_pair ? pair_off[r0] : 0, pb = has_pair ? pair_off[r1] - pb0 : 0;
+        const int64_t tb0 = J.text_off[r0], tb = J.text_off[r1] - tb0;
+        const int64_t pb0 = has_pair ? J.pair_off[r0] : 0, pb = has_pair ? J.pair_off[r1] - pb0 : 0;
         // Offsets stay absolute (as in the caller's buffer): the chunk is copied to dev + (tb0 & 15) and the base
         // pointer is shifted by -tb0, so that base + 16k is 16-byte aligned, as the kernel's LDG.128 needs.
         const int64_t ta = tb0 & 15, pa = pb0 & 15;
         CUF(d->text.ensure((size_t)tb + 96)); CUF(d->toff.ensure((size_t)(m + 1) * 8));
-        if (tb) CUF(cudaMemcpyAsync(d->text.as<uint8_t>() + ta, text + tb0, (size_t)tb, cudaMemcpyHostToDevice, st));
-        CUF(cudaMemcpyAsync(d->toff.p, text_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (tb) CUF(cudaMemcpyAsync(d->text.as<uint8_t>() + ta, J.text + tb0, (size_t)tb, cudaMemcpyHostToDevice, st));
+        CUF(cudaMemcpyAsync(d->toff.p, J.text_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
         if (has_pair) {
             CUF(d->pair.ensure((size_t)pb + 96)); CUF(d->poff.ensure((size_t)(m + 1) * 8));
-            if (pb) CUF(cudaMemcpyAsync(d->pair.as<uint8_t>() + pa, pair + pb0, (size_t)pb, cudaMemcpyHostToDevice, st));
-            CUF(cudaMemcpyAsync(d->poff.p, pair_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (pb) CUF(cudaMemcpyAsync(d->pair.as<uint8_t>() + pa, J.pair + pb0, (size_t)pb, cudaMemcpyHostToDevice, st));
+            CUF(cudaMemcpyAsync(d->poff.p, J.pair_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
         }
         Side a{d->text.as<uint8_t>() + ta - tb0, d->toff.as<int64_t>(), tb};
         Side b{has_pair ? d->pair.as<uint8_t>() + pa - pb0 : nullptr, d->poff.as<int64_t>(), pb};
@@ -663,7 +639,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
             if (want_tt) { CUF(d->tt.ensure(tot)); P.token_type_ids = d->tt.as<int8_t>(); }
             if (want_seq) { CUF(d->seq.ensure(tot)); P.sequence_id = d->seq.as<int8_t>(); }
             if (has_pair) { CUF(d->seq_len.ensure((size_t)m * 4)); CUF(d->status.ensure((size_t)m)); P.seq_len = d->seq_len.as<int32_t>(); P.row_status = d->status.as<uint8_t>(); }
-            FAIL_RC(encode_fixed_on_device(h, d, st, a, has_pair ? &b : nullptr, m, max_len, flags, P));
+            FAIL_RC(encode_fixed_on_device(h, d, st, a, has_pair ? &b : nullptr, m, max_len, J.flags, P));
             const size_t o0 = (size_t)r0 * (size_t)max_len;
             CUF(cudaMemcpyAsync(out->input_ids + o0, d->ids.p, tot * 4, cudaMemcpyDeviceToHost, st));
             CUF(cudaMemcpyAsync(out->attention_mask + o0, d->mask.p, tot, cudaMemcpyDeviceToHost, st));
@@ -679,13 +655,13 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         }
 
         // ---- ragged layout ---------------------------------------------------------------------------
-        if (tb + pb + 16 > h->max_chunk_bytes) FAIL_RC(fail(h, GENZTOK_E_LIMIT, "chunk too large"));
+        if (tb + pb + 16 > h->max_chunk_bytes) PFAIL(GENZTOK_E_LIMIT, "chunk too large")
         CUF(d->redo.ensure((size_t)m * 4)); CUF(d->fix.ensure((size_t)m * 4));
         CUF(d->L.ensure((size_t)m * 4)); CUF(d->keep.ensure((size_t)m * 4)); CUF(d->out_len.ensure((size_t)m * 8));
         CUF(d->row_off.ensure((size_t)(m + 1) * 8)); CUF(d->tail.ensure((size_t)m));
         FAIL_RC(launch_guard(h, d, st, tb + pb + 16, 0));
         RowArgs A{};
-        A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = flags;
+        A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = J.flags;
         A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8;
         if (want_spans) {
             CUF(d->nwA.ensure((size_t)m * 4)); CUF(d->nwB.ensure((size_t)m * 4)); CUF(d->span_cnt.ensure((size_t)m * 8)); CUF(d->span_off.ensure((size_t)(m + 1) * 8));
@@ -696,7 +672,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         FAIL_RC(launch_bpe(h, d, st));
         RowArgs R = A; R.row_list = d->redo.as<uint32_t>();
         FAIL_RC(launch_rows<MODE_COUNT>(h, d, R, st, "k_rows_count_redo", std::min<int64_t>(m, (int64_t)d->sm_count * 64)));
-        LenArgs LA{d->L.as<int32_t>(), m, (int32_t)has_max_len, has_max_len ? max_len : 0, padding ? 1 : 0, truncation ? 1 : 0,
+        LenArgs LA{d->L.as<int32_t>(), m, (int32_t)has_max_len, has_max_len ? max_len : 0, J.padding ? 1 : 0, J.truncation ? 1 : 0,
                    d->keep.as<int32_t>(), d->out_len.as<int64_t>(), d->tail.as<uint8_t>(),
                    want_spans ? d->nwA.as<int32_t>() : nullptr, (want_spans && has_pair) ? d->nwB.as<int32_t>() : nullptr,
                    want_spans ? d->span_cnt.as<int64_t>() : nullptr};
@@ -721,29 +697,29 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         Q.ids = d->ids.as<int32_t>(); Q.row_off = d->row_off.as<int64_t>(); Q.n_rows = m; Q.keep = d->keep.as<int32_t>(); Q.tail = d->tail.as<uint8_t>();
         Q.mask = d->mask.as<uint8_t>(); Q.has_pair = has_pair; Q.row_len = d->row_len.as<int32_t>();
         if (has_pair) { Q.tt = d->tt.as<int8_t>(); Q.seq = d->seq.as<int8_t>(); Q.tt_len = d->tt_len.as<int32_t>(); Q.seq_len = d->seq_len.as<int32_t>(); Q.status = d->status.as<uint8_t>(); }
-        Q.has_max_len = has_max_len; Q.max_len = has_max_len ? max_len : 0; Q.padding = padding ? 1 : 0; Q.truncation = truncation ? 1 : 0; Q.eos_i8 = eos8;
+        Q.has_max_len = has_max_len; Q.max_len = has_max_len ? max_len : 0; Q.padding = J.padding ? 1 : 0; Q.truncation = J.truncation ? 1 : 0; Q.eos_i8 = eos8;
         Q.tokens_ctr = d->C.ctr + C_TOKENS;
         { LaunchScope ls(h, d, "k_post_rows"); k_post_rows<<<(unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->T, Q, nullptr); }
         CUF(cudaGetLastError());
-        // bring the chunk home
-        const size_t old = r_ids.size();
-        r_ids.resize(old + (size_t)total); r_mask.resize(old + (size_t)total);
-        if (has_pair) { r_tt.resize(old + (size_t)total); r_seq.resize(old + (size_t)total); }
+        // bring the chunk home; offsets are kept relative to this device's part
+        const size_t old = part->ids.size();
+        part->ids.resize(old + (size_t)total); part->mask.resize(old + (size_t)total);
+        if (has_pair) { part->tt.resize(old + (size_t)total); part->seq.resize(old + (size_t)total); }
         std::vector<int64_t> offs((size_t)m + 1);
         if (total) {
-            CUF(cudaMemcpyAsync(r_ids.data() + old, d->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-            CUF(cudaMemcpyAsync(r_mask.data() + old, d->mask.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(part->ids.data() + old, d->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(part->mask.data() + old, d->mask.p, (size_t)total, cudaMemcpyDeviceToHost, st));
             if (has_pair) {
-                CUF(cudaMemcpyAsync(r_tt.data() + old, d->tt.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-                CUF(cudaMemcpyAsync(r_seq.data() + old, d->seq.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+                CUF(cudaMemcpyAsync(part->tt.data() + old, d->tt.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+                CUF(cudaMemcpyAsync(part->seq.data() + old, d->seq.p, (size_t)total, cudaMemcpyDeviceToHost, st));
             }
         }
         std::vector<int64_t> soffs;
         if (want_spans) {
             soffs.resize((size_t)m + 1);
-            const size_t so = r_spans.size();
-            r_spans.resize(so + (size_t)span_n * 2);
-            if (span_n) CUF(cudaMemcpyAsync(r_spans.data() + so, d->spans.p, (size_t)span_n * 8, cudaMemcpyDeviceToHost, st));
+            const size_t so = part->spans.size();
+            part->spans.resize(so + (size_t)span_n * 2);
+            if (span_n) CUF(cudaMemcpyAsync(part->spans.data() + so, d->spans.p, (size_t)span_n * 8, cudaMemcpyDeviceToHost, st));
             CUF(cudaMemcpyAsync(soffs.data(), d->span_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
         CUF(cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -754,36 +730,141 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
             CUF(cudaMemcpyAsync(out->row_status + r0, d->status.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         }
         CUF(cudaStreamSynchronize(st));
-        for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = ragged_total + offs[(size_t)i];
-        ragged_total += total;
-        if (want_spans) { for (int64_t i = 1; i <= m; i++) out->span_off[r0 + i] = span_total + soffs[(size_t)i]; span_total += span_n; }
+        for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = part->total + offs[(size_t)i];      // relative to the part
+        part->total += total;
+        if (want_spans) { for (int64_t i = 1; i <= m; i++) out->span_off[r0 + i] = part->span_total + soffs[(size_t)i]; part->span_total += span_n; }
     }
     unsigned long long tokens_after = 0, nerr = 0;
     CUF(cudaMemcpyAsync(&tokens_after, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaMemcpyAsync(&nerr, d->C.ctr + C_ERR, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaStreamSynchronize(st));
-    if (nerr) FAIL_RC(fail(h, GENZTOK_E_CUDA, "internal error: device pipeline reported %llu inconsistencies", nerr));
-    out->real_tokens = (int64_t)(tokens_after - tokens_before);
-    if (fixed) {
-        if (want_tt) for (int64_t r = 0; r < n; r++) out->tt_len[r] = max_len;
-    } else {
-        out->total = ragged_total;
-        auto keepv = [&](auto& vec, auto** dst) {
-            using E = typename std::remove_reference<decltype(vec)>::type::value_type;
-            E* p = (E*)malloc(std::max<size_t>(vec.size() * sizeof(E), 16));
-            if (!vec.empty()) memcpy(p, vec.data(), vec.size() * sizeof(E));
-            ob->mallocs.push_back(p);
-            *dst = p;
-        };
-        keepv(r_ids, &out->input_ids); keepv(r_mask, &out->attention_mask);
-        if (has_pair) { keepv(r_tt, &out->token_type_ids); keepv(r_seq, &out->sequence_id); }
-        if (want_spans) keepv(r_spans, &out->spans);
-    }
-    return GENZTOK_OK;
-#undef OOM_CHECK
+    if (nerr) PFAIL(GENZTOK_E_CUDA, "internal error: device pipeline reported %llu inconsistencies", nerr)
+    part->tokens = (int64_t)(tokens_after - tokens_before);
+#undef PFAIL
 #undef FAIL_RC
 #undef CUF
 }
+
+}  // namespace
+
+extern "C" {
+
+int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, const uint8_t* pair, const int64_t* pair_off, int64_t n,
+                   int32_t max_len, int padding, int truncation, uint32_t flags, genztok_encoded_t* out) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (!out || n < 0 || !text_off) return fail(h, GENZTOK_E_INVALID, "genztok_encode: bad arguments");
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    memset(out, 0, sizeof *out);
+    std::lock_guard<std::mutex> lk(h->mu);
+    EncodeJob J{};
+    J.text = text; J.text_off = text_off; J.pair = pair; J.pair_off = pair_off;
+    J.max_len = max_len; J.padding = padding; J.truncation = truncation; J.flags = flags; J.out = out;
+    J.has_pair = pair_off != nullptr;
+    J.has_max_len = max_len != GENZTOK_MAX_LEN_NONE;
+    J.want_spans = (flags & GENZTOK_WANT_SPANS) != 0;       // return_offset: produced by the ragged pipeline
+    J.fixed = J.has_max_len && max_len >= 1 && padding && truncation && fixed_fits(h->devs[0], max_len) && !J.want_spans;
+    J.want_tt = J.has_pair && (flags & GENZTOK_WANT_TOKEN_TYPE);
+    J.want_seq = J.has_pair && (flags & GENZTOK_WANT_SEQUENCE_ID);
+    const bool has_pair = J.has_pair, fixed = J.fixed;
+    OutBlock* ob = new OutBlock();
+    out->_owner = ob;
+    out->n = n; out->has_pair = has_pair;
+    auto free_nolock = [&]() {
+        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        for (void* p : ob->mallocs) free(p);
+        delete ob;
+        memset(out, 0, sizeof *out);
+    };
+#define OOM_CHECK(p) if (!(p)) { free_nolock(); return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
+    if (J.want_spans) { out->span_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->span_off); out->span_off[0] = 0; }
+    if (fixed) {
+        const size_t tot = (size_t)n * (size_t)max_len;
+        out->width = max_len; out->total = (int64_t)tot;
+        out->input_ids = out_alloc<int32_t>(h, ob, tot); OOM_CHECK(out->input_ids);
+        out->attention_mask = out_alloc<uint8_t>(h, ob, tot); OOM_CHECK(out->attention_mask);
+        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
+        if (J.want_tt) { out->token_type_ids = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->token_type_ids); out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len); }
+        if (J.want_seq) { out->sequence_id = out_alloc<int8_t>(h, ob, tot); OOM_CHECK(out->sequence_id); }
+        if (has_pair) { out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len); out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status); }
+    } else {
+        out->width = 0;
+        out->row_off = out_alloc<int64_t>(h, ob, (size_t)n + 1); OOM_CHECK(out->row_off);
+        out->row_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->row_len);
+        if (has_pair) {
+            out->seq_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->seq_len);
+            out->tt_len = out_alloc<int32_t>(h, ob, (size_t)n); OOM_CHECK(out->tt_len);
+            out->row_status = out_alloc<uint8_t>(h, ob, (size_t)n); OOM_CHECK(out->row_status);
+        }
+        out->row_off[0] = 0;
+    }
+#undef OOM_CHECK
+
+    // Shard by document across the handle's devices: contiguous row ranges balanced by bytes, one host
+    // thread per device, no collective; every device writes its own rows of the result.
+    const int G = (int)h->devs.size();
+    std::vector<int64_t> dcut((size_t)G + 1, n);
+    dcut[0] = 0;
+    {
+        auto weight = [&](int64_t r) { return text_off[r] + (has_pair ? pair_off[r] : 0) + 64 * r; };
+        const int64_t wtot = weight(n) - weight(0);
+        for (int g = 1; g < G; g++) {
+            const int64_t want = weight(0) + wtot * g / G;
+            int64_t lo = dcut[(size_t)g - 1], hi = n;
+            while (lo < hi) { int64_t mid = (lo + hi) / 2; if (weight(mid) < want) lo = mid + 1; else hi = mid; }
+            dcut[(size_t)g] = lo;
+        }
+    }
+    std::vector<EncodePart> parts((size_t)G);
+    if (G == 1 || n < 2 * G) {
+        if (G > 1) { for (int g = 1; g <= G; g++) dcut[(size_t)g] = n; }
+        encode_rows_on_device(h, h->devs[0], J, 0, n, &parts[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() { encode_rows_on_device(h, h->devs[(size_t)g], J, dcut[(size_t)g], dcut[(size_t)g + 1], &parts[(size_t)g]); });
+        for (auto& t : th) t.join();
+    }
+    for (auto& pt : parts)
+        if (pt.rc) { free_nolock(); { std::lock_guard<std::mutex> l(h->err_mu); h->err = pt.err; } return pt.rc; }
+    out->real_tokens = 0;
+    for (auto& pt : parts) out->real_tokens += pt.tokens;
+    if (fixed) {
+        if (J.want_tt) for (int64_t r = 0; r < n; r++) out->tt_len[r] = max_len;
+    } else {
+        // stitch the parts: shift every part's row offsets by what came before it, concatenate the flat planes
+        int64_t base = 0, sbase = 0;
+        size_t ntot = 0, stot = 0;
+        for (auto& pt : parts) { ntot += pt.ids.size(); stot += pt.spans.size(); }
+        int32_t* ids = (int32_t*)malloc(std::max<size_t>(ntot * 4, 16)); ob->mallocs.push_back(ids);
+        uint8_t* mask = (uint8_t*)malloc(std::max<size_t>(ntot, 16)); ob->mallocs.push_back(mask);
+        int8_t *tt = nullptr, *seq = nullptr; int32_t* spans = nullptr;
+        if (has_pair) { tt = (int8_t*)malloc(std::max<size_t>(ntot, 16)); ob->mallocs.push_back(tt); seq = (int8_t*)malloc(std::max<size_t>(ntot, 16)); ob->mallocs.push_back(seq); }
+        if (J.want_spans) { spans = (int32_t*)malloc(std::max<size_t>(stot * 4, 16)); ob->mallocs.push_back(spans); }
+        for (int g = 0; g < G; g++) {
+            EncodePart& pt = parts[(size_t)g];
+            const int64_t rb = (G == 1 || n < 2 * G) ? (g == 0 ? 0 : n) : dcut[(size_t)g], re = (G == 1 || n < 2 * G) ? n : dcut[(size_t)g + 1];
+            if (base) for (int64_t r = rb + 1; r <= re; r++) out->row_off[r] += base;
+            if (J.want_spans && sbase) for (int64_t r = rb + 1; r <= re; r++) out->span_off[r] += sbase;
+            if (!pt.ids.empty()) {
+                memcpy(ids + base, pt.ids.data(), pt.ids.size() * 4);
+                memcpy(mask + base, pt.mask.data(), pt.mask.size());
+                if (has_pair) { memcpy(tt + base, pt.tt.data(), pt.tt.size()); memcpy(seq + base, pt.seq.data(), pt.seq.size()); }
+            }
+            if (J.want_spans && !pt.spans.empty()) memcpy(spans + 2 * sbase, pt.spans.data(), pt.spans.size() * 4);
+            base += pt.total; sbase += pt.span_total;
+        }
+        out->total = base;
+        out->input_ids = ids; out->attention_mask = mask; out->token_type_ids = tt; out->sequence_id = seq; out->spans = spans;
+    }
+    return GENZTOK_OK;
+}
+
+}  // extern "C"
+
+namespace {
+}  // namespace
+
+extern "C" {
 
 // ---- decode -------------------------------------------------------------------------------------------
 int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,

@@ -307,3 +307,26 @@ def test_config5_custom_vocab_long_documents(oracle):
         assert_matches_oracle(be, ref, what="config5 pairs")
         dec = tok.decode_batch(be["input_ids"][:8])
         assert dec == orc.decode_batch(be["input_ids"][:8].reshape(-1), np.arange(0, 8 * 4096 + 1, 4096, dtype=np.int64))
+
+
+def test_one_handle_many_devices(oracle):
+    # SURVEY.md 8e inside one process: a handle created over several GPUs shards the rows by document
+    # (one host thread per GPU, no collective) and the stitched result equals the single-GPU one
+    import torch
+    from genz_tokenize_b200 import Tokenize, workload
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    multi = Tokenize(devices=list(range(ndev)))
+    assert multi._lib.genztok_device_count(multi._h) == ndev
+    t = workload.generate(601, 20000, 0, 13, 0.05)
+    p = workload.generate(5601, 20000, 0, 13, 0.05)
+    for kw in (dict(max_len=64), dict(), dict(max_len=9, padding=False)):
+        be = multi.encode_batch(t, p, **kw)
+        orc = oracle.encode_batch(t, p, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="multi-device %r" % (kw,))
+    be = multi.encode_batch(t, None, return_offset=True)
+    orc = oracle.encode_batch(t, None, return_offset=True, threads=8)
+    assert np.array_equal(be["span_off"], orc["span_off"]) and np.array_equal(be["spans"], orc["span"])
+    few = multi.encode_batch((t[0][:t[1][3]], t[1][:4]), max_len=16)       # fewer rows than 2 x devices: one device does it all
+    assert np.array_equal(few["input_ids"].reshape(-1), oracle.encode_batch((t[0][:t[1][3]], t[1][:4]), None, max_len=16)["ids"])
