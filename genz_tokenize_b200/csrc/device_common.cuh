@@ -25,6 +25,7 @@ struct DevTables {
     // decode forms (tokenize.py:137-139)
     const uint8_t* form_blob;
     const uint32_t *mid_off, *mid_len, *last_off, *last_len;
+    const uint32_t *mid_desc, *last_desc;   // (offset/8) << 8 | min(len,255)
     int32_t n_ids;
 };
 

@@ -67,7 +67,7 @@ struct DeviceCtx {
     // chunk workspace
     DevBuf text, toff, pair, poff;                // inputs
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
-    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans;
+    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
     // profiling
     bool profiling = false;
@@ -183,6 +183,8 @@ int init_device(genztok_t* h, DeviceCtx* d) {
     CU(upload(d, H.mid_len, &T.mid_len));
     CU(upload(d, H.last_off, &T.last_off));
     CU(upload(d, H.last_len, &T.last_len));
+    CU(upload(d, H.mid_desc, &T.mid_desc));
+    CU(upload(d, H.last_desc, &T.last_desc));
     T.n_ids = (int32_t)H.n_ids;
     T.pad = H.special_id[0]; T.bos = H.special_id[1]; T.eos = H.special_id[2]; T.msk = H.special_id[3]; T.unk = H.special_id[4];
     T.specials_distinct = (T.pad != T.bos && T.pad != T.eos && T.bos != T.eos) ? 1 : 0;
@@ -278,6 +280,25 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
 int launch_bpe(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     LaunchScope ls(h, d, "k_bpe_pending");
     k_bpe_pending<<<d->sm_count * 4, 256, 0, st>>>(d->T, d->C);
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+// out[0..n] = exclusive scan of in[0..n): one block for small inputs, tiles + totals + fix-up otherwise
+int launch_scan(genztok_t* h, DeviceCtx* d, cudaStream_t st, const int64_t* in, int64_t* out, int64_t n) {
+    if (n <= 2 * SCAN_TILE) {
+        LaunchScope ls(h, d, "k_scan_i64");
+        k_scan_i64<<<1, 1024, 0, st>>>(in, out, n);
+        CU(cudaGetLastError());
+        return GENZTOK_OK;
+    }
+    const int64_t nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CU(d->scan_tmp.ensure((size_t)(2 * nt + 2) * 8));
+    int64_t* tsum = d->scan_tmp.as<int64_t>();
+    int64_t* texcl = tsum + nt;
+    { LaunchScope ls(h, d, "k_scan_tiles"); k_scan_tiles<<<(unsigned)nt, 1024, 0, st>>>(in, out, tsum, n); }
+    { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(tsum, texcl, nt); }
+    { LaunchScope ls(h, d, "k_scan_fix"); k_scan_fix<<<(unsigned)nt, 1024, 0, st>>>(out, texcl, n, nt); }
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
@@ -401,7 +422,7 @@ void genztok_destroy(genztok_t* h) {
         if (d->stream) cudaStreamSynchronize(d->stream);
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
-                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->slots,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->slots,
                           &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -677,10 +698,10 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
                    want_spans ? d->nwA.as<int32_t>() : nullptr, (want_spans && has_pair) ? d->nwB.as<int32_t>() : nullptr,
                    want_spans ? d->span_cnt.as<int64_t>() : nullptr};
         { LaunchScope ls(h, d, "k_row_lens"); k_row_lens<<<(unsigned)std::min<int64_t>((m + 255) / 256, 4096), 256, 0, st>>>(LA); }
-        { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), m); }
+        FAIL_RC(launch_scan(h, d, st, d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), m));
         int64_t total = 0, span_n = 0;
         if (want_spans) {
-            { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->span_cnt.as<int64_t>(), d->span_off.as<int64_t>(), m); }
+            FAIL_RC(launch_scan(h, d, st, d->span_cnt.as<int64_t>(), d->span_off.as<int64_t>(), m));
             CUF(cudaMemcpyAsync(&span_n, d->span_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st));
         }
         CUF(cudaMemcpyAsync(&total, d->row_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st));
@@ -883,8 +904,7 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
         CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
         A.out_len = d->out_len.as<int64_t>();
         if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode<false><<<grid, 256, 0, st>>>(d->T, A); }
-        { LaunchScope ls(h, d, "k_scan_i64"); k_scan_i64<<<1, 1024, 0, st>>>(d->out_len.as<int64_t>(), d_out_off, n); }
-        CU(cudaGetLastError());
+        { int rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d_out_off, n); if (rc) return rc; }
         if (total_bytes) {
             CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));

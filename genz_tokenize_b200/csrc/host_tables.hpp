@@ -18,6 +18,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -82,6 +83,7 @@ struct HostTables {
     // entry n_ids is the form of any id outside the decoder (the unk STRING, :123-124)
     std::vector<uint8_t> form_blob;
     std::vector<uint32_t> mid_off, mid_len, last_off, last_len;
+    std::vector<uint32_t> mid_desc, last_desc;    // (offset/8) << 8 | min(len,255): one load per id on the device
     int64_t n_ids = 0;
 
     std::string err;
@@ -318,16 +320,24 @@ struct HostTables {
             cp_slots[i] = CpEntry{kv.first, kv.second.first, kv.second.second, 0};
         }
 
-        // ---- decode forms
+        // ---- decode forms (each form starts on an 8-byte boundary so that the kernel can fetch it with 8-byte loads)
         mid_off.resize((size_t)n_ids + 1); mid_len.resize((size_t)n_ids + 1);
         last_off.resize((size_t)n_ids + 1); last_len.resize((size_t)n_ids + 1);
+        auto put = [&](const std::string& f, uint32_t* off, uint32_t* len) {
+            while (form_blob.size() % 8) form_blob.push_back(0);
+            *off = (uint32_t)form_blob.size(); *len = (uint32_t)f.size();
+            form_blob.insert(form_blob.end(), f.begin(), f.end());
+        };
         for (int64_t id = 0; id <= n_ids; id++) {
             const std::string& piece = (id < n_ids && decoder[(size_t)id] >= 0) ? enc_keys[(size_t)decoder[(size_t)id]] : special[4];
-            std::string m = replace_cont(piece + " "), l = replace_cont(piece);
-            mid_off[(size_t)id] = (uint32_t)form_blob.size(); mid_len[(size_t)id] = (uint32_t)m.size();
-            form_blob.insert(form_blob.end(), m.begin(), m.end());
-            last_off[(size_t)id] = (uint32_t)form_blob.size(); last_len[(size_t)id] = (uint32_t)l.size();
-            form_blob.insert(form_blob.end(), l.begin(), l.end());
+            put(replace_cont(piece + " "), &mid_off[(size_t)id], &mid_len[(size_t)id]);
+            put(replace_cont(piece), &last_off[(size_t)id], &last_len[(size_t)id]);
+        }
+        // one 32-bit descriptor per form: (offset / 8) << 8 | min(len, 255)
+        mid_desc.resize((size_t)n_ids + 1); last_desc.resize((size_t)n_ids + 1);
+        for (int64_t id = 0; id <= n_ids; id++) {
+            mid_desc[(size_t)id] = ((mid_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(mid_len[(size_t)id], 255u);
+            last_desc[(size_t)id] = ((last_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(last_len[(size_t)id], 255u);
         }
         while (form_blob.size() % 16) form_blob.push_back(0);
         return true;

@@ -67,6 +67,40 @@ __global__ void __launch_bounds__(1024) k_scan_i64(const int64_t* in, int64_t* o
     if (threadIdx.x == 0) out[n] = carry_s;
 }
 
+// Large inputs: tile-local scans + a scan of the tile totals + a fix-up pass.
+static const int SCAN_TILE = 4096;          // elements per block (1024 threads x 4)
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int64_t* in, int64_t* out, int64_t* tile_sum, int64_t n) {
+    __shared__ int64_t warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+    int64_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    int64_t x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(FULL_MASK, x, o); if (lane >= o) x += t; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = warp_sums[lane], y = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int64_t t = __shfl_up_sync(FULL_MASK, y, o); if (lane >= o) y += t; }
+        warp_sums[lane] = y - w;
+        if (lane == 31) tile_sum[blockIdx.x] = y;
+    }
+    __syncthreads();
+    int64_t run = warp_sums[wid] + x - s;       // exclusive prefix of this thread inside the tile
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+__global__ void __launch_bounds__(1024) k_scan_fix(int64_t* out, const int64_t* tile_excl, int64_t n, int64_t n_tiles) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+    const int64_t add = tile_excl[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < n) out[base + k] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tile_excl[n_tiles];
+}
+
 struct PostArgs {
     int32_t* ids;              // flat
     const int64_t* row_off;    // NULL -> fixed layout, row r at r*W
@@ -187,8 +221,10 @@ struct DecArgs {
 
 __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool last, uint32_t* off, uint32_t* len) {
     const uint32_t k = (id >= 0 && id < T.n_ids) ? (uint32_t)id : (uint32_t)T.n_ids;   // decoder.get(i, unk_token)
-    *off = last ? T.last_off[k] : T.mid_off[k];
-    *len = last ? T.last_len[k] : T.mid_len[k];
+    const uint32_t dsc = last ? T.last_desc[k] : T.mid_desc[k];
+    *off = (dsc >> 8) * 8u;
+    *len = dsc & 255u;
+    if (*len == 255u) *len = last ? T.last_len[k] : T.mid_len[k];                       // very long vocab entry
 }
 
 static const int DEC_CAP = 2048;       // bytes staged per warp before a flush
@@ -256,7 +292,12 @@ __global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
             if (!big) {
                 if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
                 uint8_t* d = ob + cur + (incl - len);
-                for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+                for (uint32_t k0 = 0; k0 < len; k0 += 8) {              // forms are 8-byte aligned in the blob: one load per 8 bytes
+                    uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);
+                    const uint32_t nb = len - k0 < 8u ? len - k0 : 8u;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; k++) if (k < nb) d[k0 + k] = (uint8_t)(v >> (8 * k));
+                }
                 cur += (int)tot;
             } else {                                        // rare: a very long vocab entry -> write this batch directly
                 if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */

@@ -195,6 +195,10 @@ def test_decode_roundtrip_batch(tok, oracle):
     assert texts == ref
     rag = tok.encode_batch(t, p)
     assert tok.decode_batch(rag["input_ids"], rag["row_off"]) == oracle.decode_batch(rag["input_ids"], rag["row_off"], threads=8)
+    # more rows than one scan tile: the multi-block offset scan
+    t2 = workload.generate(302, 30000, 0, 9, 0.02)
+    big = tok.encode_batch(t2, max_len=16)
+    assert tok.decode_batch(big["input_ids"]) == oracle.decode_batch(big["input_ids"].reshape(-1), np.arange(0, 30000 * 16 + 1, 16, dtype=np.int64), threads=8)
 
 
 def test_device_api_matches_host_api(tok):
