@@ -6,6 +6,7 @@ All tokenisation runs in hand-written sm_100a CUDA kernels inside libgenztok.so 
 include/genztok.h); this package is the thin ctypes wrapper plus the synthetic-workload
 generator used by the benchmark.  There is no CPU fallback.
 """
+from . import preprocess
 from .tokenizer import BatchEncoding, GenztokError, Tokenize, pack_strings
 
-__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings"]
+__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings", "preprocess"]

@@ -30,6 +30,7 @@
 #include "encode.cuh"
 #include "host_tables.hpp"
 #include "post.cuh"
+#include "prep.cuh"
 
 using namespace gzt;
 
@@ -67,7 +68,7 @@ struct DeviceCtx {
     // chunk workspace
     DevBuf text, toff, pair, poff;                // inputs
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
-    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp;
+    DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
     // profiling
     bool profiling = false;
@@ -422,7 +423,7 @@ void genztok_destroy(genztok_t* h) {
         if (d->stream) cudaStreamSynchronize(d->stream);
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
-                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->slots,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->slots,
                           &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -979,6 +980,64 @@ int genztok_decode(genztok_t* h, const int32_t* ids, const int64_t* ids_off, int
         return rc;
     }
     bytes = (uint8_t*)malloc(std::max<size_t>(acc.size(), 16));
+    if (!acc.empty()) memcpy(bytes, acc.data(), acc.size());
+    ob->mallocs.push_back(bytes);
+    out->n = n; out->total = total_all; out->bytes = bytes; out->off = off; out->_owner = ob;
+    return GENZTOK_OK;
+}
+
+// ---- preprocess.py normalisers ------------------------------------------------------------------------------
+int genztok_preprocess(genztok_t* h, int op, const uint8_t* text, const int64_t* text_off, int64_t n, genztok_text_t* out) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (!out || n < 0 || !text_off || op < 0 || op > 4) return fail(h, GENZTOK_E_INVALID, "genztok_preprocess: bad arguments");
+    if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
+    memset(out, 0, sizeof *out);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[0];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    LaunchScope::cur_stream = st;
+    OutBlock* ob = new OutBlock();
+    int64_t* off = out_alloc<int64_t>(h, ob, (size_t)n + 1);
+    if (!off) { delete ob; return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
+    off[0] = 0;
+    std::vector<uint8_t> acc;
+    int64_t total_all = 0;
+    int rc = GENZTOK_OK;
+    auto bail = [&](int code) { for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; } delete ob; return code; };
+    int64_t r0 = 0;
+    while (r0 < n) {
+        int64_t r1 = std::min<int64_t>(n, r0 + h->chunk_rows);
+        while (r1 > r0 + 1 && text_off[r1] - text_off[r0] > h->max_chunk_bytes) r1 = r0 + (r1 - r0) / 2;
+        const int64_t m = r1 - r0, b0 = text_off[r0], nb = text_off[r1] - b0;
+        cudaError_t e;
+        if ((e = d->text.ensure((size_t)nb + 64)) != cudaSuccess || (e = d->toff.ensure((size_t)(m + 1) * 8)) != cudaSuccess ||
+            (e = d->out_len.ensure((size_t)m * 8)) != cudaSuccess || (e = d->row_off.ensure((size_t)(m + 1) * 8)) != cudaSuccess)
+            return bail(fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)));
+        if (nb) cudaMemcpyAsync(d->text.p, text + b0, (size_t)nb, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d->toff.p, text_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st);
+        PrepArgs A{d->text.as<uint8_t>() - b0, d->toff.as<int64_t>(), m, op, d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), nullptr};
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 7) / 8, (int64_t)d->sm_count * 8));
+        { LaunchScope ls(h, d, "k_prep_len"); k_prep<false><<<grid, 256, 0, st>>>(A); }
+        rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d->row_off.as<int64_t>(), m);
+        if (rc) return bail(rc);
+        int64_t total = 0;
+        cudaMemcpyAsync(&total, d->row_off.as<int64_t>() + m, 8, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(fail(h, GENZTOK_E_CUDA, "preprocess: %s", cudaGetErrorString(e)));
+        if ((e = d->prep_out.ensure((size_t)total + 64)) != cudaSuccess) return bail(fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)));
+        A.out = d->prep_out.as<uint8_t>();
+        { LaunchScope ls(h, d, "k_prep_write"); k_prep<true><<<grid, 256, 0, st>>>(A); }
+        std::vector<int64_t> offs((size_t)m + 1);
+        const size_t old = acc.size();
+        acc.resize(old + (size_t)total);
+        if (total) cudaMemcpyAsync(acc.data() + old, d->prep_out.p, (size_t)total, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return bail(fail(h, GENZTOK_E_CUDA, "preprocess: %s", cudaGetErrorString(e)));
+        for (int64_t i = 1; i <= m; i++) off[r0 + i] = total_all + offs[(size_t)i];
+        total_all += total;
+        r0 = r1;
+    }
+    uint8_t* bytes = (uint8_t*)malloc(std::max<size_t>(acc.size(), 16));
     if (!acc.empty()) memcpy(bytes, acc.data(), acc.size());
     ob->mallocs.push_back(bytes);
     out->n = n; out->total = total_all; out->bytes = bytes; out->off = off; out->_owner = ob;

@@ -158,6 +158,15 @@ int genztok_sequence_id(genztok_t *h, const int32_t *ids, int64_t n, int apply_t
 /* get_atttention_mask (tokenize.py:148-152) */
 int genztok_attention_mask(genztok_t *h, const int32_t *ids, int64_t n, uint8_t *out);
 
+/* ---- text normalisers of genz_tokenize/preprocess.py, the optional step before Tokenize ------ */
+#define GENZTOK_PREP_REMOVE_HTML 0        /* remove_html        preprocess.py:5-9   */
+#define GENZTOK_PREP_CONVERT_UNICODE 1    /* convert_unicode    preprocess.py:30-36 */
+#define GENZTOK_PREP_REMOVE_PUNCTUATIONS 2 /* remove_punctuations preprocess.py:39-44 */
+#define GENZTOK_PREP_REMOVE_EMOJI 3       /* remove_emoji       preprocess.py:47-72 */
+#define GENZTOK_PREP_REMOVE_URL 4         /* remove_URL         preprocess.py:75-80 */
+/* One normaliser over a batch of documents (packed UTF-8 + offsets in, the same out). */
+int genztok_preprocess(genztok_t *h, int op, const uint8_t *text, const int64_t *text_off, int64_t n, genztok_text_t *out);
+
 /* ---- utilities -------------------------------------------------------------------------------- */
 void *genztok_host_alloc(size_t bytes); /* pinned host memory for inputs */
 void genztok_host_free(void *p);

@@ -69,6 +69,8 @@ def _load():
         L.gzo_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(_Text)]
         L.gzo_free_text.argtypes = [C.POINTER(_Text)]
         L.gzo_max_threads.restype = C.c_int
+        L.gzo_preprocess.restype = C.c_int
+        L.gzo_preprocess.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Text)]
         _lib = L
     return _lib
 
@@ -90,6 +92,21 @@ def _arr(ptr, n, dtype):
 
 def _opt(x):
     return None if x == -1 else int(x)
+
+
+def preprocess(op, texts):
+    """preprocess.py normalisers (0 remove_html, 1 convert_unicode, 2 remove_punctuations, 3 remove_emoji, 4 remove_URL)."""
+    L = _load()
+    tb, to = texts if isinstance(texts, tuple) else pack_strings(texts)
+    n = len(to) - 1
+    out = _Text()
+    L.gzo_preprocess(int(op), tb.ctypes.data, to.ctypes.data, n, C.byref(out))
+    try:
+        o = _arr(out.off, n + 1, np.int64)
+        b = _arr(out.bytes, int(o[-1]), np.uint8).tobytes()
+    finally:
+        L.gzo_free_text(C.byref(out))
+    return [b[o[i]:o[i + 1]].decode("utf-8", "surrogatepass") for i in range(n)]
 
 
 class Oracle:
