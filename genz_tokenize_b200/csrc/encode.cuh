@@ -713,17 +713,22 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             if (qn > 0) {
                 const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
                 const bool pairs_planes = A.has_pair && (A.tt || A.seq);
-                for (int d = 0; d < nd; d++) {
-                    const uint32_t em = ts->demit[d];
-                    if (em & EM_SKIP) continue;
-                    for (int32_t q = lane; q < qn; q += 32) {
-                        const int32_t i0 = (KQ + q) * 4;
-                        const size_t g = grow + (size_t)d * W + i0;
-                        st_cs128(A.ids + g, pad4);
-                        if (A.mask) st_cs32(A.mask + g, 0u);
+                // which rows to skip / which need computed token types, as warp-uniform bit masks (no per-row loads)
+                uint32_t em_l = lane < nd ? ts->demit[lane] : EM_SKIP;
+                const uint32_t skip_rows = __ballot_sync(FULL_MASK, (em_l & EM_SKIP) != 0);
+                const uint32_t long_rows = __ballot_sync(FULL_MASK, (em_l & EM_SEQLONG) != 0);
+                for (int32_t q = lane; q < qn; q += 32) {               // column block: usually a single pass
+                    const int32_t i0 = (KQ + q) * 4;
+                    int32_t* gi = A.ids + grow + i0;
+                    uint8_t* gm = A.mask ? A.mask + grow + i0 : nullptr;
+                    for (int d = 0; d < nd; d++, gi += W) {
+                        if ((skip_rows >> d) & 1u) continue;
+                        st_cs128(gi, pad4);
+                        if (gm) st_cs32(gm + (size_t)d * W, 0u);
                         if (pairs_planes) {
                             uint32_t ttw = 0u, sqw = 0xFEFEFEFEu;
-                            if (em & EM_SEQLONG) seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                            if ((long_rows >> d) & 1u) seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                            const size_t g = grow + (size_t)d * W + i0;
                             if (A.tt) st_cs32(A.tt + g, ttw);
                             if (A.seq) st_cs32(A.seq + g, sqw);
                         }
