@@ -19,9 +19,36 @@
 // row; the D rows are staged in shared memory and written with 16-byte streaming stores by the whole warp.
 // Rows that met a word whose BPE is still pending are queued for a second pass (k_bpe_pending in between).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "device_common.cuh"
 
 namespace gzt {
+
+// ---- TMA write-out (MODE_FIXED) --------------------------------------------------------------------
+// The [n, W] planes are written by the TMA unit instead of by store instructions: per tile of D rows the warp stages
+// the first KR columns (the only ones that can hold real tokens) in shared memory in their final form and one lane
+// issues 2-D tensor stores -- box [D x KR] from the staging area, box(es) [D x PB] for the pad columns from a
+// block-wide constant buffer.  Rows that do not fit KR columns are queued for the generic second pass.
+struct __align__(64) TmaPlanes {
+    CUtensorMap ids_real, ids_pad, mask_real, mask_pad, tt_real, tt_pad;
+    int32_t KR;   // staged columns per row (multiple of 16, <= W)
+    int32_t PB;   // columns per pad box (multiple of 16; 0 = no pad columns)
+};
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+                 "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__host__ __device__ __forceinline__ size_t r128(size_t x) { return (x + 127) & ~(size_t)127; }
+// bytes of one staging buffer (ids int32 + mask [+ token types]) for D rows of KR columns, every plane 128-byte aligned
+__host__ __device__ __forceinline__ size_t tma_stage_bytes(int D, int KR, bool pair) { return r128((size_t)D * KR * 4) + r128((size_t)D * KR) * (pair ? 2 : 1); }
+// bytes of the block-wide constant pad buffers ([D x PB] pad ids + [D x PB] zero bytes)
+__host__ __device__ __forceinline__ size_t tma_const_bytes(int D, int PB) { return r128((size_t)D * PB * 4) + r128((size_t)D * PB); }
 
 enum RowMode { MODE_FIXED = 0, MODE_COUNT = 1, MODE_RAGGED = 2 };
 
@@ -363,11 +390,12 @@ __device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t
 
 // ---- walking one side of a tile --------------------------------------------------------------------
 // All 32 lanes call this.  ts->doff[0..nd] holds the side's document offsets relative to the tile base `tb`
-// (16-byte aligned), ts->dpos[] the next token position of every row.  Tokens at positions < limit are delivered to
-// rowbufs (FIXED) / ts->rg.dout (RAGGED).  All byte positions are 32-bit offsets from tb.
+// (16-byte aligned), ts->dpos[] the next token position of every row.  Tokens at positions < cap (<= limit) are
+// delivered to rowbufs (FIXED) / ts->rg.dout (RAGGED); words of a row that has reached `limit` are not looked up.
+// All byte positions are 32-bit offsets from tb.
 template <int MODE, typename TokT>
 __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C, const uint8_t* __restrict__ tb, TileSmem* ts, int nd,
-                                          int lane, int32_t limit, TokT* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
+                                          int lane, int32_t limit, int32_t cap, TokT* rowbufs, int32_t Wp, int32_t* ids_out, bool insert_ok, int32_t* spans, bool count_words) {
     const int32_t S = ts->doff[0], E = ts->doff[nd];
     if (E <= S) return;
     // documents that are empty share their start with the next one: then the per-piece start bits cannot number
@@ -512,7 +540,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             }
             if (MODE != MODE_COUNT && has && nt) {
                 TokT* dsts = nullptr; int32_t* dstg = nullptr; int32_t lim;
-                if (MODE == MODE_FIXED) { dsts = rowbufs + (size_t)doc * Wp; lim = limit; }
+                if (MODE == MODE_FIXED) { dsts = rowbufs + (size_t)doc * Wp; lim = cap; }
                 else { dstg = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }
                 uint32_t fl = 0;
                 if (nt == 1) {
@@ -539,16 +567,31 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
     __syncwarp();
 }
 
-// TokT: type of the rows staged in shared memory (uint16_t when every id fits: half the footprint, twice the blocks)
-template <int MODE, typename TokT>
-__global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+// TokT: type of the rows staged in shared memory (uint16_t when every id fits: half the footprint, twice the blocks).
+// TMA (MODE_FIXED, TokT = int32_t only): the planes are written by tensor stores from a final-form staging area (see TmaPlanes).
+template <int MODE, typename TokT, bool TMA>
+__global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A, const __grid_constant__ TmaPlanes M) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D;
-    const int32_t Wp = (W + 3) & ~3;
-    const size_t per_warp = sizeof(TileSmem) + (MODE == MODE_FIXED ? (((size_t)D * Wp * sizeof(TokT) + 15) & ~(size_t)15) : 0);
-    TileSmem* ts = reinterpret_cast<TileSmem*>(smem_raw + (size_t)wib * per_warp);
-    TokT* rowbufs = reinterpret_cast<TokT*>(reinterpret_cast<uint8_t*>(ts) + sizeof(TileSmem));
+    const int32_t KR = TMA ? M.KR : 0, PB = TMA ? M.PB : 0;
+    const int32_t Wp = TMA ? KR : ((W + 3) & ~3);
+    const bool tma_tt = TMA && A.has_pair && A.tt;
+    const size_t stage_b = TMA ? tma_stage_bytes(D, KR, tma_tt) : 0;
+    const size_t const_b = TMA && PB ? tma_const_bytes(D, PB) : 0;
+    const size_t per_warp = TMA ? r128(sizeof(TileSmem)) + 2 * stage_b
+                                : sizeof(TileSmem) + (MODE == MODE_FIXED ? (((size_t)D * Wp * sizeof(TokT) + 15) & ~(size_t)15) : 0);
+    TileSmem* ts = reinterpret_cast<TileSmem*>(smem_raw + const_b + (size_t)wib * per_warp);
+    uint8_t* const stage0 = reinterpret_cast<uint8_t*>(ts) + (TMA ? r128(sizeof(TileSmem)) : sizeof(TileSmem));
+    TokT* rowbufs = reinterpret_cast<TokT*>(stage0);
+    if (TMA && PB) {                                               // block-wide constants: pad ids, zero bytes
+        const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
+        uint4* cp = reinterpret_cast<uint4*>(smem_raw);
+        const int n_pad = (int)(r128((size_t)D * PB * 4) >> 4), n_all = (int)(const_b >> 4);
+        for (int i = threadIdx.x; i < n_all; i += blockDim.x) cp[i] = i < n_pad ? pad4 : make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
 
     const uint32_t n_items = (uint32_t)(A.row_list ? C.ctr[C_REDO] : (unsigned long long)A.n_rows);   // rows per chunk < 2^31
     // a row list holds arbitrary rows: they are not contiguous in the text, so its tiles hold one document
@@ -556,7 +599,9 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
     const uint32_t n_tiles = (n_items + Dt - 1) / Dt;
     const uint32_t n_warps = gridDim.x * (uint32_t)wpb;
     const int32_t limit = MODE == MODE_FIXED ? W - 1 : 0x7FFFFFFF;
+    const int32_t cap = TMA ? min(limit, KR) : limit;            // positions that are staged
     const bool insert_ok = !A.row_list && MODE != MODE_RAGGED;   // second passes only look words up
+    uint32_t tma_iter = 0;
     uint32_t tok_total = 0;
     for (uint32_t tile = blockIdx.x * (uint32_t)wpb + wib; tile < n_tiles; tile += n_warps) {
         const int64_t r0 = A.row_list ? (int64_t)A.row_list[tile] : (int64_t)(tile * Dt);
@@ -570,12 +615,21 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         if (lane <= nd) ts->doff[lane] = (int32_t)(o64 - tbase);
         if (nd == 32 && lane == 0) ts->doff[32] = (int32_t)(o32nd - tbase);
         const bool count_words = MODE != MODE_FIXED && ((MODE == MODE_COUNT && A.nwA) || (MODE == MODE_RAGGED && A.spans));
+        if (TMA) {
+            // this tile's staging buffer: free once the stores issued two tiles ago have read it; every id starts as pad
+            rowbufs = reinterpret_cast<TokT*>(stage0 + (tma_iter & 1u) * stage_b);
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
+            for (int i = lane; i < D * (KR >> 2); i += 32) reinterpret_cast<uint4*>(rowbufs)[i] = pad4;
+            __syncwarp();
+        }
         if (lane < nd) {
             ts->dpos[lane] = 1;                                    // position 0 is <s> (tokenize.py:135)
             ts->dflag[lane] = 0;
             ts->rg.dwrd[lane] = 0;
             if (MODE == MODE_RAGGED && A.spans) { ts->rg.dsbase[lane] = A.span_off[r0 + lane]; ts->rg.dshift[lane] = 0; }
-            if (MODE == MODE_FIXED) { if (limit > 0) rowbufs[(size_t)lane * Wp] = (TokT)T.bos; }
+            if (MODE == MODE_FIXED) { if (cap > 0) rowbufs[(size_t)lane * Wp] = (TokT)T.bos; }
             if (MODE == MODE_RAGGED) {
                 const int64_t ro = A.row_off[r0 + lane];
                 const int32_t kp = A.keep[r0 + lane];
@@ -584,13 +638,13 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             }
         }
         __syncwarp();
-        walk_side<MODE, TokT>(T, C, A.a.bytes + tbase, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+        walk_side<MODE, TokT>(T, C, A.a.bytes + tbase, ts, nd, lane, limit, cap, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         if (A.has_pair) {
             // ... </s> </s> B   (tokenize.py:237-239)
             if (lane < nd) {
                 const int32_t pos = ts->dpos[lane];
                 ts->dnA[lane] = pos - 1;
-                if (MODE == MODE_FIXED) { TokT* rb = rowbufs + (size_t)lane * Wp; if (pos < limit) rb[pos] = (TokT)T.eos; if (pos + 1 < limit) rb[pos + 1] = (TokT)T.eos; }
+                if (MODE == MODE_FIXED) { TokT* rb = rowbufs + (size_t)lane * Wp; if (pos < cap) rb[pos] = (TokT)T.eos; if (pos + 1 < cap) rb[pos + 1] = (TokT)T.eos; }
                 if (MODE == MODE_RAGGED) { int32_t* g = A.ids + ts->rg.dout[lane]; const int32_t kp = ts->rg.dkeep[lane]; if (pos < kp) g[pos] = T.eos; if (pos + 1 < kp) g[pos + 1] = T.eos; }
                 ts->dpos[lane] = pos + 2;
                 if (count_words) {
@@ -617,16 +671,21 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
             if (lane <= nd) ts->doff[lane] = (int32_t)(o64 - tbase);
             if (nd == 32 && lane == 0) ts->doff[32] = (int32_t)(p32nd - tbase);
             __syncwarp();
-            walk_side<MODE, TokT>(T, C, A.b.bytes + tbase, ts, nd, lane, limit, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
+            walk_side<MODE, TokT>(T, C, A.b.bytes + tbase, ts, nd, lane, limit, cap, rowbufs, Wp, A.ids, insert_ok, A.spans, count_words);
         }
         // ---- closing </s>, row bookkeeping (one lane per row)
         if (lane < nd) {
             const int32_t pos = ts->dpos[lane];
             const int32_t dL = pos + 1;                                // framed length (>= W when the walk stopped early)
-            if (MODE == MODE_FIXED) { if (pos < limit) rowbufs[(size_t)lane * Wp + pos] = (TokT)T.eos; }
+            if (MODE == MODE_FIXED) { if (pos < cap) rowbufs[(size_t)lane * Wp + pos] = (TokT)T.eos; }
             if (MODE == MODE_RAGGED) { if (pos < ts->rg.dkeep[lane]) A.ids[ts->rg.dout[lane] + pos] = T.eos; }
             const uint32_t fl = ts->dflag[lane];
-            if (fl & F_DIRTY) {
+            SeqDesc sd;
+            if (MODE == MODE_FIXED && A.has_pair) sd = seq_describe(ts->dnA[lane], dL, W);
+            bool again = (fl & F_DIRTY) != 0;
+            // TMA write-out: rows that need more than the KR staged columns, or a mask by value, take the generic second pass
+            if (TMA) again |= (KR < W && (dL > KR || (A.has_pair && sd.m > KR))) || (fl & F_PADTOK);
+            if (again) {
                 if (!A.row_list) { const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL); A.redo_list[k] = (uint32_t)(r0 + lane); }
                 else atomicAdd(&C.ctr[C_ERR], 1ULL);   // cannot happen: every word of a redo row was inserted in pass 1
                 if (MODE == MODE_FIXED) ts->demit[lane] = EM_SKIP;
@@ -634,10 +693,10 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                 const int64_t dr = r0 + lane;
                 const int32_t Lr = dL < W ? dL : W;
                 ts->demit[lane] = (uint32_t)Lr | (dL >= W ? EM_TRUNC : 0u) | ((fl & F_PADTOK) ? EM_GENERIC : 0u);
+                if (TMA && dL >= W) rowbufs[(size_t)lane * Wp + (W - 1)] = (TokT)T.eos;   // tokens[:max_len-1] + [eos] (KR == W here)
                 if (A.row_len) A.row_len[dr] = Lr;
                 if (!(fl & F_PADTOK)) tok_total += (uint32_t)Lr;       // rows with a pad id inside are counted from their mask
                 if (A.has_pair) {
-                    const SeqDesc sd = seq_describe(ts->dnA[lane], dL, W);
                     ts->dsd[lane] = sd;
                     if (sd.m > Lr) ts->demit[lane] |= EM_SEQLONG;       // token types run on over the pads
                     if (A.seq_len) A.seq_len[dr] = sd.m;
@@ -659,6 +718,45 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         }
         __syncwarp();
         if (MODE != MODE_FIXED) continue;
+        if (TMA) {
+            // ---- FIXED, TMA: mask (and token types) of the staged columns, then tensor stores issued by one lane
+            uint8_t* const sm_mask = reinterpret_cast<uint8_t*>(rowbufs) + r128((size_t)D * KR * 4);
+            uint8_t* const sm_tt = sm_mask + r128((size_t)D * KR);
+            const int32_t qpr = KR >> 2;                                // quads per staged row
+            for (int d = lane >> 2; d < D; d += 8) {
+                const uint32_t em = d < nd ? ts->demit[d] : EM_SKIP;
+                const int32_t Lr = (em & EM_SKIP) ? 0 : (int32_t)(em & EM_LEN);
+                for (int32_t q = lane & 3; q < qpr; q += 4) {
+                    const int32_t c = Lr - q * 4;
+                    const uint32_t mk = c >= 4 ? 0x01010101u : (c <= 0 ? 0u : (0x01010101u & ((1u << (8 * c)) - 1)));
+                    reinterpret_cast<uint32_t*>(sm_mask)[d * qpr + q] = mk;
+                    if (tma_tt) {
+                        uint32_t ttw = 0, sqw;
+                        if (!(em & EM_SKIP)) seq_words4(ts->dsd[d], q * 4, W, A.eos_i8, &ttw, &sqw);
+                        reinterpret_cast<uint32_t*>(sm_tt)[d * qpr + q] = ttw;
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const int32_t r = (int32_t)r0;
+                tma_store_2d(&M.ids_real, rowbufs, 0, r);
+                tma_store_2d(&M.mask_real, sm_mask, 0, r);
+                if (tma_tt) tma_store_2d(&M.tt_real, sm_tt, 0, r);
+                if (PB) {
+                    const uint8_t* zeros = smem_raw + r128((size_t)D * PB * 4);
+                    for (int32_t c0 = KR; c0 < W; c0 += PB) {
+                        tma_store_2d(&M.ids_pad, smem_raw, c0, r);
+                        tma_store_2d(&M.mask_pad, zeros, c0, r);
+                        if (tma_tt) tma_store_2d(&M.tt_pad, zeros, c0, r);
+                    }
+                }
+                bulk_commit();
+            }
+            tma_iter++;
+            continue;
+        }
         // ---- FIXED: the warp writes its rows -----------------------------------------------------------
         if ((W & 15) == 0) {
             // Pass A: the quads that can hold real tokens (the first KQ of every row), 8 rows x 4 quads per step with
@@ -760,6 +858,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
         }
         __syncwarp();
     }
+    if (TMA) { if (lane == 0) bulk_wait<0>(); __syncwarp(); }   // shared memory must outlive the stores' reads
     if (MODE == MODE_FIXED) {
         tok_total = __reduce_add_sync(FULL_MASK, tok_total);   // < 2^32 per warp
         if (lane == 0 && tok_total) atomicAdd(&C.ctr[C_TOKENS], (unsigned long long)tok_total);

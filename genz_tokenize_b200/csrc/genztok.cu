@@ -59,7 +59,7 @@ struct DeviceCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     DevTables T{};
     WordCache C{};
     bool cache_ready = false;
@@ -91,6 +91,8 @@ struct genztok {
     int64_t force_group = 0;
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
+    int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
+    int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
     std::map<std::string, std::pair<int64_t, double>> prof_acc;
     // pinned host pool
@@ -169,6 +171,7 @@ int init_device(genztok_t* h, DeviceCtx* d) {
     CU(cudaGetDeviceProperties(&prop, d->device));
     d->sm_count = prop.multiProcessorCount;
     d->smem_optin = prop.sharedMemPerBlockOptin;
+    d->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     const HostTables& H = h->H;
     DevTables& T = d->T;
@@ -235,15 +238,18 @@ int pick_tile_docs(genztok_t* h, const DeviceCtx* d, int64_t bytes_a, int64_t by
     return D;
 }
 
-template <int MODE, typename TokT>
-int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
+template <int MODE, typename TokT, bool TMA>
+int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint, const TmaPlanes* M) {
     const int D = A.row_list ? 1 : A.D;
-    auto smem_for = [&](int w) { return (size_t)w * (sizeof(TileSmem) + (MODE == MODE_FIXED ? row_stage_bytes(d, A.W, A.D) : 0)); };
+    auto smem_for = [&](int w) {
+        if (TMA) return (M->PB ? tma_const_bytes(A.D, M->PB) : 0) + (size_t)w * (r128(sizeof(TileSmem)) + 2 * tma_stage_bytes(A.D, M->KR, A.has_pair && A.tt));
+        return (size_t)w * (sizeof(TileSmem) + (MODE == MODE_FIXED ? row_stage_bytes(d, A.W, A.D) : 0));
+    };
     int wpb = 8;
     while (wpb > 1 && smem_for(wpb) > d->smem_optin) wpb >>= 1;
     const size_t smem = smem_for(wpb);
     if (smem > d->smem_optin) return fail(h, GENZTOK_E_LIMIT, "row of %d ids does not fit shared memory", A.W);
-    auto kern = k_rows<MODE, TokT>;
+    auto kern = k_rows<MODE, TokT, TMA>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
@@ -251,15 +257,68 @@ int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st,
     const int64_t tiles = (n_items_hint + D - 1) / D;
     int64_t blocks = std::min<int64_t>((tiles + wpb - 1) / wpb, (int64_t)d->sm_count * occ * h->grid_mult);
     if (blocks < 1) blocks = 1;
+    static const TmaPlanes no_planes{};
     LaunchScope ls(h, d, name);
-    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(d->T, d->C, A);
+    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(d->T, d->C, A, TMA ? *M : no_planes);
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
 template <int MODE>
-int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint) {
-    if (MODE == MODE_FIXED && narrow_ids(d)) return launch_rows_t<MODE, uint16_t>(h, d, A, st, name, n_items_hint);
-    return launch_rows_t<MODE, int32_t>(h, d, A, st, name, n_items_hint);
+int launch_rows(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st, const char* name, int64_t n_items_hint, const TmaPlanes* M = nullptr) {
+    if (MODE == MODE_FIXED && M) return launch_rows_t<MODE_FIXED, int32_t, true>(h, d, A, st, name, n_items_hint, M);
+    if (MODE == MODE_FIXED && narrow_ids(d)) return launch_rows_t<MODE, uint16_t, false>(h, d, A, st, name, n_items_hint, nullptr);
+    return launch_rows_t<MODE, int32_t, false>(h, d, A, st, name, n_items_hint, nullptr);
+}
+
+// ---- TMA write-out set-up (see TmaPlanes in encode.cuh) -------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// map of a row-major [n, W] plane with boxes of [rows x cols] elements
+bool plane_map(CUtensorMap* m, void* base, int elt_bytes, int64_t n, int32_t W, int cols, int rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * (cuuint64_t)elt_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, elt_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// Decide whether this launch can use the TMA write-out and describe the planes.  KR (staged columns) follows the
+// average text per row: ~3 bytes per token plus framing, at least 32; rows that need more take the generic second pass.
+bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes, TmaPlanes* M) {
+    if (h->no_tma || A.row_list || !A.ids || !A.mask || A.seq || A.n_rows < 1 || A.n_rows >= (1ll << 31)) return false;
+    const int32_t W = A.W;
+    if (W < 16 || (W & 15)) return false;
+    auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+    if (misaligned(A.ids) || misaligned(A.mask) || (A.has_pair && A.tt && misaligned(A.tt))) return false;
+    int64_t KR = h->force_kr;
+    if (KR <= 0) KR = std::max<int64_t>(32, (bytes / A.n_rows / 3 + 12 + (A.has_pair ? 4 : 0) + 15) & ~15ll);
+    if (KR + 16 > W) KR = W;
+    if (KR > 256) return false;
+    const int32_t PB = (int32_t)std::min<int64_t>(W - KR, 256);
+    const bool tt = A.has_pair && A.tt;
+    // the kernel is latency bound: the staging must not cost occupancy (four 8-warp blocks per SM), else the store path wins
+    if (!h->force_kr && 4 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(sizeof(TileSmem)) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_per_sm) return false;
+    if (2 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(sizeof(TileSmem)) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_optin) return false;
+    memset(M, 0, sizeof *M);
+    M->KR = (int32_t)KR; M->PB = PB;
+    bool ok = plane_map(&M->ids_real, A.ids, 4, A.n_rows, W, (int)KR, A.D) && plane_map(&M->mask_real, A.mask, 1, A.n_rows, W, (int)KR, A.D);
+    if (ok && tt) ok = plane_map(&M->tt_real, A.tt, 1, A.n_rows, W, (int)KR, A.D);
+    if (ok && PB) {
+        ok = plane_map(&M->ids_pad, A.ids, 4, A.n_rows, W, PB, A.D) && plane_map(&M->mask_pad, A.mask, 1, A.n_rows, W, PB, A.D);
+        if (ok && tt) ok = plane_map(&M->tt_pad, A.tt, 1, A.n_rows, W, PB, A.D);
+    }
+    return ok;
 }
 
 // Can the fixed-layout kernel stage one row of W ids (one document per tile, one warp per block)?
@@ -331,7 +390,9 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>();
     A.eos_i8 = eos_as_i8(d);
     A.D = pick_tile_docs(h, d, a.nbytes, b ? b->nbytes : 0, n, W, true);
-    rc = launch_rows<MODE_FIXED>(h, d, A, st, "k_rows_fixed", n);
+    TmaPlanes M;
+    const bool tma = setup_tma(h, d, A, bytes, &M);
+    rc = launch_rows<MODE_FIXED>(h, d, A, st, tma ? "k_rows_fixed_tma" : "k_rows_fixed", n, tma ? &M : nullptr);
     if (rc) return rc;
     rc = launch_bpe(h, d, st);
     if (rc) return rc;
@@ -497,6 +558,11 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "wide_rows") {
         h->force_wide = value;
         for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
+    } else if (n == "no_tma") {
+        h->no_tma = value;
+    } else if (n == "tma_columns") {
+        if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "tma_columns must be 0 (auto) or a multiple of 16 up to 256");
+        h->force_kr = value;
     } else return fail(h, GENZTOK_E_INVALID, "unknown option %s", n.c_str());
     return GENZTOK_OK;
 }

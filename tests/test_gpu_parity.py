@@ -185,6 +185,30 @@ def test_every_tile_size_and_small_chunks(oracle, group):
         assert_matches_oracle(be, orc, what="group %d seed %d" % (group, seed))
 
 
+@pytest.mark.parametrize("variant", [(1, 0, 0), (0, 16, 0), (0, 32, 3), (0, 48, 8), (0, 64, 0), (0, 256, 5), (0, 0, 32)],
+                         ids=lambda v: "no_tma%d-cols%d-group%d" % v)
+def test_tma_writeout_variants(oracle, variant):
+    # the fixed planes written by the TMA unit (k_rows<FIXED, TMA>): every staged width (rows that do not fit take the
+    # generic second pass), tile sizes, partial last tiles, against the store-instruction path and the oracle
+    from genz_tokenize_b200 import Tokenize, workload
+    no_tma, cols, group = variant
+    tok = Tokenize()
+    tok.set_option("no_tma", no_tma)
+    tok.set_option("tma_columns", cols)
+    tok.set_option("group", group)
+    tok.set_profiling(True)
+    for seed, n, lo, hi, noise, paired, kw in [(701, 3001, 3, 13, 0.02, False, dict(max_len=128)), (702, 2999, 3, 13, 0.02, True, dict(max_len=256)),
+                                               (703, 2000, 0, 9, 0.2, True, dict(max_len=16)), (704, 1000, 10, 60, 0.05, True, dict(max_len=96)),
+                                               (705, 1500, 0, 40, 0.1, False, dict(max_len=32)), (706, 700, 100, 300, 0.02, False, dict(max_len=512))]:
+        t = workload.generate(seed, n, lo, hi, noise)
+        p = workload.generate(seed + 5000, n, lo, hi, noise) if paired else None
+        be = tok.encode_batch(t, p, **kw)
+        orc = oracle.encode_batch(t, p, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="tma variant %r seed %d" % (variant, seed))
+    kernels = tok.profile_report()
+    assert ("k_rows_fixed_tma" in kernels) == (not no_tma), sorted(kernels)
+
+
 def test_decode_roundtrip_batch(tok, oracle):
     from genz_tokenize_b200 import workload
     t = workload.generate(301, 4000, 3, 13, 0.02)
