@@ -45,7 +45,7 @@ static const uint32_t SLOT_LOCKED = 0xFFFFFFFFu;
 static const uint32_t KEY_INLINE = 24;
 static const uint32_t VAL_PENDING = 0u, VAL_SINGLE = 1u << 30, VAL_MULTI = 2u << 30, VAL_KIND = 3u << 30, VAL_PAYLOAD = (1u << 30) - 1;
 
-enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_COUNT = 16 };
+enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_FLATFIX_A = 9, C_FLATFIX_B = 10, C_COUNT = 16 };
 
 struct WordCache {
     Slot* slots;
@@ -89,13 +89,14 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
 // murmur finaliser.  (Every lookup verifies the full key, so quality only affects probe length.)
 __device__ __forceinline__ uint32_t hash_key24(uint64_t k0, uint64_t k1, uint64_t k2, uint32_t len) {
     uint32_t h = len * 0x9E3779B1u;
-    h ^= (uint32_t)k0 * 0xcc9e2d51u;
-    h ^= (uint32_t)(k0 >> 32) * 0x1b873593u;
-    h ^= (uint32_t)k1 * 0x85ebca6bu;
-    h ^= (uint32_t)(k1 >> 32) * 0xc2b2ae35u;
-    h ^= (uint32_t)k2 * 0x27d4eb2fu;
-    h ^= (uint32_t)(k2 >> 32) * 0x165667b1u;
-    return fmix32(h);
+    h += (uint32_t)k0 * 0xcc9e2d51u;
+    h += (uint32_t)(k0 >> 32) * 0x1b873593u;
+    h += (uint32_t)k1 * 0x85ebca6bu;
+    h += (uint32_t)(k1 >> 32) * 0xc2b2ae35u;
+    h += (uint32_t)k2 * 0x27d4eb2fu;
+    h += (uint32_t)(k2 >> 32) * 0x165667b1u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+    return h;
 }
 // 64-bit hash of a long key, 8 bytes at a time (unaligned bytes gathered bytewise only for the tail)
 __device__ __forceinline__ uint64_t hash_long(const uint8_t* p, uint32_t len) {

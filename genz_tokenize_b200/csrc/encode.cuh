@@ -258,9 +258,60 @@ __device__ __forceinline__ void key_from_pieces(const uint4& v0, const uint4& v1
     *k0 = r0; *k1 = r1; *k2 = r2;
 }
 
+// ... and from 40 bytes (two pieces and the next 8 bytes): any word of up to 24 bytes whatever its alignment
+__device__ __forceinline__ void key_from_pieces40(const uint4& v0, const uint4& v1, const uint2& v2, int sh, uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    uint64_t q0 = ((uint64_t)v0.y << 32) | v0.x, q1 = ((uint64_t)v0.w << 32) | v0.z, q2 = ((uint64_t)v1.y << 32) | v1.x, q3 = ((uint64_t)v1.w << 32) | v1.z;
+    uint64_t q4 = ((uint64_t)v2.y << 32) | v2.x;
+    if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; sh -= 8; }
+    uint64_t r0 = q0, r1 = q1, r2 = q2;
+    if (sh) {
+        const int s8 = sh * 8;
+        r0 = (q0 >> s8) | (q1 << (64 - s8));
+        r1 = (q1 >> s8) | (q2 << (64 - s8));
+        r2 = (q2 >> s8) | (q3 << (64 - s8));
+    }
+    if (len <= 8) { if (len < 8) r0 &= (1ULL << (len * 8)) - 1; r1 = 0; r2 = 0; }
+    else if (len <= 16) { if (len < 16) r1 &= (1ULL << ((len - 8) * 8)) - 1; r2 = 0; }
+    else if (len < 24) r2 &= (1ULL << ((len - 16) * 8)) - 1;
+    *k0 = r0; *k1 = r1; *k2 = r2;
+}
+
+// the 24 bytes at byte offset sh of a 40-byte window, not yet zero padded
+__device__ __forceinline__ void key_from_pieces40_nomask(const uint4& v0, const uint4& v1, const uint2& v2, int sh, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    uint64_t q0 = ((uint64_t)v0.y << 32) | v0.x, q1 = ((uint64_t)v0.w << 32) | v0.z, q2 = ((uint64_t)v1.y << 32) | v1.x, q3 = ((uint64_t)v1.w << 32) | v1.z;
+    uint64_t q4 = ((uint64_t)v2.y << 32) | v2.x;
+    if (sh >= 8) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; sh -= 8; }
+    uint64_t r0 = q0, r1 = q1, r2 = q2;
+    if (sh) {
+        const int s8 = sh * 8;
+        r0 = (q0 >> s8) | (q1 << (64 - s8));
+        r1 = (q1 >> s8) | (q2 << (64 - s8));
+        r2 = (q2 >> s8) | (q3 << (64 - s8));
+    }
+    *k0 = r0; *k1 = r1; *k2 = r2;
+}
+// zero the key bytes from len on (len in 1..24), branch free on 32-bit halves
+__device__ __forceinline__ void key_mask24(uint32_t len, uint64_t* k0, uint64_t* k1, uint64_t* k2) {
+    auto m32 = [&](int i) -> uint32_t {
+        const int nb = min(max((int)len - 4 * i, 0), 4);
+        return nb ? (0xFFFFFFFFu >> (8 * (4 - nb))) : 0u;
+    };
+    *k0 &= ((uint64_t)m32(1) << 32) | m32(0);
+    *k1 &= ((uint64_t)m32(3) << 32) | m32(2);
+    *k2 &= ((uint64_t)m32(5) << 32) | m32(4);
+}
+
 __device__ __noinline__ bool long_key_equal(const uint8_t* kp, const uint8_t* wptr, uint32_t len) {
-    for (uint32_t i = 0; i < len; i++) if (kp[i] != wptr[i]) return false;
-    return true;
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) {                 // eight independent byte pairs per step (one round trip, not eight)
+        uint32_t diff = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) diff |= (uint32_t)kp[i + k] ^ (uint32_t)wptr[i + k];
+        if (diff) return false;
+    }
+    uint32_t diff = 0;
+    for (; i < len; i++) diff |= (uint32_t)kp[i] ^ (uint32_t)wptr[i];
+    return diff == 0;
 }
 
 // Find the word in the cache or insert it (BPE pending).  Returns the slot's value word (VAL_*).

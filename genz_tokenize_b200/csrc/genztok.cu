@@ -28,6 +28,7 @@
 #include "bpe.cuh"
 #include "device_common.cuh"
 #include "encode.cuh"
+#include "flat.cuh"
 #include "host_tables.hpp"
 #include "post.cuh"
 #include "prep.cuh"
@@ -70,6 +71,7 @@ struct DeviceCtx {
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
     DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
+    struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok, fixa, fixp; } flat[2];   // byte-parallel pipeline, per side
     // profiling
     bool profiling = false;
     std::vector<ProfEvent> events;
@@ -91,6 +93,11 @@ struct genztok {
     int64_t force_group = 0;
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
+    int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
+    int64_t flat_rows = 8;               // rows per warp tile of k_flat_rows
+    int64_t cache_slots_log2 = 0;        // EXPERIMENT: fixed word-cache size (no worst-case guarantee)
+    int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
+    int64_t rows_minb = 4, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
     int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
     int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
@@ -200,7 +207,7 @@ uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p
 int ensure_cache(genztok_t* h, DeviceCtx* d) {
     if (d->cache_ready) return GENZTOK_OK;
     const uint64_t B = (uint64_t)h->max_chunk_bytes;
-    const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
+    const uint64_t slots = h->cache_slots_log2 > 0 ? (1ull << h->cache_slots_log2) : std::max<uint64_t>(next_pow2(B), 1024);
     CU(d->slots.ensure(slots * sizeof(Slot)));
     CU(d->key_arena.ensure(B + 64));
     CU(d->tok_arena.ensure((2 * B + 64) * 4));
@@ -295,7 +302,7 @@ bool plane_map(CUtensorMap* m, void* base, int elt_bytes, int64_t n, int32_t W, 
 }
 // Decide whether this launch can use the TMA write-out and describe the planes.  KR (staged columns) follows the
 // average text per row: ~3 bytes per token plus framing, at least 32; rows that need more take the generic second pass.
-bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes, TmaPlanes* M) {
+bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes, TmaPlanes* M, size_t tile_bytes = sizeof(TileSmem)) {
     if (h->no_tma || A.row_list || !A.ids || !A.mask || A.seq || A.n_rows < 1 || A.n_rows >= (1ll << 31)) return false;
     const int32_t W = A.W;
     if (W < 16 || (W & 15)) return false;
@@ -307,9 +314,14 @@ bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes
     if (KR > 256) return false;
     const int32_t PB = (int32_t)std::min<int64_t>(W - KR, 256);
     const bool tt = A.has_pair && A.tt;
-    // the kernel is latency bound: the staging must not cost occupancy (four 8-warp blocks per SM), else the store path wins
-    if (!h->force_kr && 4 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(sizeof(TileSmem)) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_per_sm) return false;
-    if (2 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(sizeof(TileSmem)) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_optin) return false;
+    if (tile_bytes == sizeof(TileSmem)) {
+        // the fused kernel is latency bound: the staging must not cost occupancy (four 8-warp blocks per SM), else the store path wins
+        if (!h->force_kr && 4 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(tile_bytes) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_per_sm) return false;
+        if (2 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(tile_bytes) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_optin) return false;
+    } else {
+        // k_flat_rows: the constant pad boxes and one row buffer per warp
+        if (2 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(tile_bytes) + r128((size_t)KR * 4)) + 1024) > d->smem_optin) return false;
+    }
     memset(M, 0, sizeof *M);
     M->KR = (int32_t)KR; M->PB = PB;
     bool ok = plane_map(&M->ids_real, A.ids, 4, A.n_rows, W, (int)KR, A.D) && plane_map(&M->mask_real, A.mask, 1, A.n_rows, W, (int)KR, A.D);
@@ -327,7 +339,7 @@ bool fixed_fits(const DeviceCtx* d, int32_t W) { return sizeof(TileSmem) + row_s
 int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
-        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
+        k_cache_guard<<<1, 1, 0, st>>>(d->C, h->cache_slots_log2 > 0 ? 1024ull : (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
@@ -365,6 +377,22 @@ int launch_scan(genztok_t* h, DeviceCtx* d, cudaStream_t st, const int64_t* in, 
 
 int8_t eos_as_i8(const DeviceCtx* d) { return (d->T.eos >= 0 && d->T.eos <= 127) ? (int8_t)d->T.eos : (int8_t)GENZTOK_EOS_MARK; }
 
+// work arrays of the byte-parallel pipeline for one side (flat.cuh)
+int flat_side_setup(genztok_t* h, DeviceCtx* d, int s, const Side& side, int64_t n, FlatSide* out) {
+    DeviceCtx::FlatBufs& B = d->flat[s];
+    const uint64_t nG = (((uint64_t)side.nbytes + 15) >> 5) + 3;            // granules (+ slack for the clamp in flat_hi)
+    const uint64_t nB = (nG + FC_OWN - 1) / FC_OWN + 1;                      // chunks
+    const uint64_t fix_cap = std::min<uint64_t>(nB * FC_BYTES, ((uint64_t)side.nbytes + (uint64_t)n) / 2 + 64);
+    const uint64_t ng = nB * FC_OWN + 2;
+    CU(B.dsb.ensure(ng * 4)); CU(B.st.ensure(ng * 4)); CU(B.tpref.ensure(ng * 2));
+    CU(B.cnt.ensure(nB * 4)); CU(B.wtok.ensure((nB << FC_SHIFT) * 4)); CU(B.fixa.ensure(fix_cap * 4)); CU(B.fixp.ensure(fix_cap * 4));
+    out->bytes = side.bytes; out->off = side.off; out->n = n;
+    out->dsb = B.dsb.as<uint32_t>(); out->st = B.st.as<uint32_t>(); out->tpref = B.tpref.as<uint16_t>(); out->cnt = B.cnt.as<uint32_t>();
+    out->wtok = B.wtok.as<uint32_t>(); out->fixa = B.fixa.as<uint32_t>(); out->fixp = B.fixp.as<uint32_t>();
+    out->fix_cap = (uint32_t)fix_cap; out->ctr_fix = s ? C_FLATFIX_B : C_FLATFIX_A; out->nB = (uint32_t)nB;
+    return GENZTOK_OK;
+}
+
 // ---- fixed layout: everything already on the device ------------------------------------------------
 int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Side& a, const Side* b, int64_t n, int32_t W, uint32_t flags,
                            const genztok_dev_planes_t& P) {
@@ -391,11 +419,71 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     A.eos_i8 = eos_as_i8(d);
     A.D = pick_tile_docs(h, d, a.nbytes, b ? b->nbytes : 0, n, W, true);
     TmaPlanes M;
-    const bool tma = setup_tma(h, d, A, bytes, &M);
-    rc = launch_rows<MODE_FIXED>(h, d, A, st, tma ? "k_rows_fixed_tma" : "k_rows_fixed", n, tma ? &M : nullptr);
-    if (rc) return rc;
-    rc = launch_bpe(h, d, st);
-    if (rc) return rc;
+    // The byte-parallel pipeline (flat.cuh) when the rows are short enough that every word matters; the fused row
+    // kernel (which stops reading a document once its row is full) otherwise.
+    bool flat = !h->no_flat && !h->no_tma && d->T.specials_distinct && a.nbytes < (1ll << 31) - 65536 && (!b || b->nbytes < (1ll << 31) - 65536) &&
+                bytes / n <= 6ll * W;
+    if (flat) {
+        RowArgs Af = A;
+        Af.D = (int32_t)h->flat_rows;
+        flat = setup_tma(h, d, Af, bytes, &M, sizeof(FlatTile));
+        if (flat) {
+            FlatRowsArgs F{};
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                rc = flat_side_setup(h, d, s, s ? *b : a, n, s ? &F.b : &F.a);
+                if (rc) return rc;
+            }
+            F.has_pair = b != nullptr; F.n_rows = n; F.W = W; F.D = Af.D; F.ids = A.ids; F.mask = A.mask; F.tt = A.tt;
+            F.row_len = A.row_len; F.seq_len = A.seq_len; F.status = A.status; F.redo_list = A.redo_list; F.fix_list = A.fix_list; F.eos_i8 = A.eos_i8;
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                const FlatSide& S = s ? F.b : F.a;
+                CU(cudaMemsetAsync(S.dsb, 0, ((size_t)S.nB * FC_OWN + 2) * 4, st));
+                { LaunchScope ls(h, d, "k_flat_doc_starts"); k_flat_doc_starts<<<(unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->C, S); }
+            }
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                const FlatSide& S = s ? F.b : F.a;
+                LaunchScope ls(h, d, "k_flat_words");
+                const unsigned per_sm = (unsigned)std::max<int64_t>(1, h->words_minb) * (8 / FW_WARPS);
+                const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)S.nB + FW_WARPS - 1) / FW_WARPS, (uint64_t)d->sm_count * per_sm);
+                switch (h->words_minb) {
+                    case 5: k_flat_words<5><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
+                    case 6: k_flat_words<6><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
+                    default: k_flat_words<4><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
+                }
+            }
+            CU(cudaGetLastError());
+            rc = launch_bpe(h, d, st);
+            if (rc) return rc;
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                const FlatSide& S = s ? F.b : F.a;
+                LaunchScope ls(h, d, "k_flat_fix"); k_flat_fix<<<d->sm_count * 4, 256, 0, st>>>(d->C, S);
+            }
+            {
+                const bool tt = F.has_pair && F.tt;
+                const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * (r128(sizeof(FlatTile)) + r128((size_t)M.KR * 4));
+                (void)tt;
+                auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 5 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
+                                       : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>));
+                if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ = 1;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+                if (occ < 1) occ = 1;
+                const int64_t tiles = (n + F.D - 1) / F.D;
+                if (h->rows_grid > 0) occ = std::min<int>(occ, (int)h->rows_grid);
+                const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)d->sm_count * occ * h->grid_mult));
+                LaunchScope ls(h, d, "k_flat_rows");
+                kern<<<(unsigned)blocks, 256, smem, st>>>(d->T, d->C, F, M);
+            }
+            CU(cudaGetLastError());
+        }
+    }
+    if (!flat) {
+        const bool tma = setup_tma(h, d, A, bytes, &M);
+        rc = launch_rows<MODE_FIXED>(h, d, A, st, tma ? "k_rows_fixed_tma" : "k_rows_fixed", n, tma ? &M : nullptr);
+        if (rc) return rc;
+        rc = launch_bpe(h, d, st);
+        if (rc) return rc;
+    }
     RowArgs R = A;
     R.row_list = d->redo.as<uint32_t>();
     rc = launch_rows<MODE_FIXED>(h, d, R, st, "k_rows_fixed_redo", std::min<int64_t>(n, (int64_t)d->sm_count * 64));
@@ -558,6 +646,19 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "wide_rows") {
         h->force_wide = value;
         for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
+    } else if (n == "no_flat") {
+        h->no_flat = value;
+    } else if (n == "flat_rows") {
+        if (value < 1 || value > 32) return fail(h, GENZTOK_E_INVALID, "flat_rows must be in 1..32");
+        h->flat_rows = value;
+    } else if (n == "cache_slots_log2") {
+        h->cache_slots_log2 = value;
+    } else if (n == "rows_grid") {
+        h->rows_grid = value;
+    } else if (n == "rows_minb") {
+        h->rows_minb = value;
+    } else if (n == "words_minb") {
+        h->words_minb = value;
     } else if (n == "no_tma") {
         h->no_tma = value;
     } else if (n == "tma_columns") {

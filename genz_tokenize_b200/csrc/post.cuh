@@ -332,7 +332,7 @@ __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsign
     const bool reset = force || (c[C_SLOTS] + need_slots) * 2 > cap || c[C_KEYS] + need_keys > C.key_cap || c[C_TOKS] + need_toks > C.tok_cap;
     c[C_RESET] = reset;
     if (reset) { c[C_SLOTS] = 0; c[C_KEYS] = 0; c[C_TOKS] = 0; }
-    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0;
+    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0;
 }
 __global__ void k_cache_clear(WordCache C) {
     if (!C.ctr[C_RESET]) return;
@@ -341,6 +341,6 @@ __global__ void k_cache_clear(WordCache C) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = z;
 }
-__global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; }
+__global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; C.ctr[C_FLATFIX_A] = 0; C.ctr[C_FLATFIX_B] = 0; }
 
 }  // namespace gzt

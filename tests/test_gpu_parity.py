@@ -185,28 +185,82 @@ def test_every_tile_size_and_small_chunks(oracle, group):
         assert_matches_oracle(be, orc, what="group %d seed %d" % (group, seed))
 
 
-@pytest.mark.parametrize("variant", [(1, 0, 0), (0, 16, 0), (0, 32, 3), (0, 48, 8), (0, 64, 0), (0, 256, 5), (0, 0, 32)],
-                         ids=lambda v: "no_tma%d-cols%d-group%d" % v)
-def test_tma_writeout_variants(oracle, variant):
-    # the fixed planes written by the TMA unit (k_rows<FIXED, TMA>): every staged width (rows that do not fit take the
-    # generic second pass), tile sizes, partial last tiles, against the store-instruction path and the oracle
+@pytest.mark.parametrize("variant", [("fused", 1, 0, 0), ("fused", 0, 16, 0), ("fused", 0, 32, 3), ("fused", 0, 48, 8), ("fused", 0, 64, 0), ("fused", 0, 256, 5),
+                                     ("fused", 0, 0, 32), ("flat", 0, 0, 8), ("flat", 0, 16, 1), ("flat", 0, 32, 5), ("flat", 0, 64, 16), ("flat", 0, 256, 4), ("flat", 0, 32, 32)],
+                         ids=lambda v: "%s-no_tma%d-cols%d-rows%d" % v)
+def test_fixed_layout_pipelines(oracle, variant):
+    # the fixed planes through every pipeline: the byte-parallel one (k_flat_words + k_flat_rows) and the fused row kernel with
+    # TMA or store-instruction write-out; every staged width (rows that do not fit take the generic second pass), tile
+    # sizes, partial last tiles, multi-token words, special ids inside the text -- all against the oracle
     from genz_tokenize_b200 import Tokenize, workload
-    no_tma, cols, group = variant
+    pipeline, no_tma, cols, rows = variant
     tok = Tokenize()
+    tok.set_option("no_flat", int(pipeline == "fused"))
     tok.set_option("no_tma", no_tma)
     tok.set_option("tma_columns", cols)
-    tok.set_option("group", group)
+    if pipeline == "fused":
+        tok.set_option("group", rows)
+    else:
+        tok.set_option("flat_rows", rows)
     tok.set_profiling(True)
     for seed, n, lo, hi, noise, paired, kw in [(701, 3001, 3, 13, 0.02, False, dict(max_len=128)), (702, 2999, 3, 13, 0.02, True, dict(max_len=256)),
                                                (703, 2000, 0, 9, 0.2, True, dict(max_len=16)), (704, 1000, 10, 60, 0.05, True, dict(max_len=96)),
-                                               (705, 1500, 0, 40, 0.1, False, dict(max_len=32)), (706, 700, 100, 300, 0.02, False, dict(max_len=512))]:
+                                               (705, 1500, 0, 40, 0.1, False, dict(max_len=32)), (706, 700, 100, 300, 0.02, False, dict(max_len=512)),
+                                               (707, 5000, 0, 3, 0.5, True, dict(max_len=16)), (708, 20000, 3, 13, 0.0, False, dict(max_len=64))]:
         t = workload.generate(seed, n, lo, hi, noise)
         p = workload.generate(seed + 5000, n, lo, hi, noise) if paired else None
         be = tok.encode_batch(t, p, **kw)
         orc = oracle.encode_batch(t, p, threads=8, **kw)
-        assert_matches_oracle(be, orc, what="tma variant %r seed %d" % (variant, seed))
+        assert_matches_oracle(be, orc, what="variant %r seed %d" % (variant, seed))
     kernels = tok.profile_report()
-    assert ("k_rows_fixed_tma" in kernels) == (not no_tma), sorted(kernels)
+    want = "k_flat_rows" if pipeline == "flat" else ("k_rows_fixed" if no_tma or not cols else "k_rows_fixed_tma")
+    assert want in kernels, sorted(kernels)
+    if pipeline == "fused":
+        assert "k_flat_rows" not in kernels
+
+
+def test_flat_pipeline_text_edges(oracle):
+    # byte-parallel pipeline on the shapes that stress its block / granule boundaries: exotic whitespace next to block ends,
+    # words across 8 KiB blocks, very long words, runs of empty documents, documents of one byte, offsets that do not start at 0
+    from genz_tokenize_b200 import Tokenize
+    from oracle.oracle import pack_strings
+    rng = np.random.default_rng(11)
+    ws = [" ", "\n", "\t", "\r\n", "\x1c", "\x85", "\xa0", "\u1680", "\u2003", "\u2028", "\u202f", "\u205f", "\u3000", "  ", " \n "]
+    near = ["\u200b", "\ufeff", "\u180e", "\xc2", "\u2040", "\u3001", "\xe1", "\u00e2\u0080"]
+    words = ["sinh_viên", "công_nghệ", "hello", "xin", "chào", "a", "b" * 23, "c" * 24, "d" * 25, "e" * 40, "ế" * 9, "thế_giới", "x" * 300, "\x00", "é"]
+    docs = []
+    for i in range(6000):
+        k = int(rng.integers(0, 12))
+        parts = []
+        for _ in range(k):
+            parts.append(words[int(rng.integers(0, len(words)))])
+            parts.append(ws[int(rng.integers(0, len(ws)))] if rng.random() < 0.9 else near[int(rng.integers(0, len(near)))])
+        docs.append("".join(parts))
+    docs += [""] * 50 + ["a"] * 300 + ["\n"] * 20 + ["y" * 9000, "z" * 70000] + ["\u2003"] * 10
+    order = rng.permutation(len(docs))
+    docs = [docs[int(i)] for i in order]
+    tok = Tokenize()
+    tok.set_profiling(True)
+    packed = pack_strings(docs)
+    for kw in (dict(max_len=64), dict(max_len=16), dict(max_len=256)):
+        be = tok.encode_batch(packed, **kw)
+        orc = oracle.encode_batch(packed, None, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="flat edges %r" % (kw,))
+        n_docs = len(packed[1]) - 1
+        lens = np.diff(packed[1])
+        ridx = np.arange(n_docs)[::-1]                                   # the same documents in reverse order as side B
+        pieces = [packed[0][packed[1][i]:packed[1][i + 1]] for i in ridx]
+        other = (np.concatenate(pieces) if pieces else packed[0][:0], np.concatenate([[0], np.cumsum(lens[ridx])]).astype(np.int64))
+        be = tok.encode_batch(packed, other, **kw)
+        orc = oracle.encode_batch(packed, other, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="flat edges pairs %r" % (kw,))
+    assert "k_flat_rows" in tok.profile_report()
+    # a chunk that starts in the middle of the caller's buffer (absolute offsets, unaligned base)
+    tok2 = Tokenize()
+    tok2.set_option("chunk_rows", 777)
+    be = tok2.encode_batch(packed, max_len=32)
+    orc = oracle.encode_batch(packed, None, threads=8, max_len=32)
+    assert_matches_oracle(be, orc, what="flat edges chunked")
 
 
 def test_decode_roundtrip_batch(tok, oracle):
