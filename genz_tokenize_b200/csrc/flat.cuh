@@ -122,6 +122,47 @@ __global__ void k_flat_doc_starts(WordCache C, FlatSide S) {
     }
 }
 
+__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_addr), "r"(c0), "r"(c1) : "memory");
+}
+// the same with an L2 eviction policy: the planes are written once and never read here, they must not push the word
+// arrays (read right after they were written) out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(m), "r"(smem_addr), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+
+// The pad columns KR..W-1 of the output planes depend on nothing: k_flat_words writes them on the side (TMA tensor stores
+// from a block-wide constant buffer, issued by one lane per chunk), while its warps wait for their probes.
+struct PadJob {
+    int32_t on;          // 0: nothing to do
+    int32_t n_tiles;     // tiles of D rows this launch writes ...
+    int32_t tile0;       // ... starting with this one
+    int32_t W, D, KR, PB;
+    int32_t want_tt;
+    int32_t pad_id;
+};
+
+// tiles [c * n_tiles / n_chunks, (c + 1) * n_tiles / n_chunks) of the pad columns; one thread.  Out of line: k_flat_words
+// is short of registers.
+__device__ __noinline__ void flat_pad_tiles(const PadJob& J, const TmaPlanes& M, uint32_t c, uint32_t n_chunks, uint32_t pad_s, uint32_t zeros_s, uint64_t l2_first) {
+    const uint32_t t0 = (uint32_t)((uint64_t)c * (uint32_t)J.n_tiles / n_chunks), t1 = (uint32_t)(((uint64_t)c + 1) * (uint32_t)J.n_tiles / n_chunks);
+    for (uint32_t t = t0; t < t1; t++) {
+        const int32_t r = (int32_t)((t + (uint32_t)J.tile0) * (uint32_t)J.D);
+        for (int32_t c0 = J.KR; c0 < J.W; c0 += J.PB) {
+            tma_store_2d_hint(&M.ids_pad, pad_s, c0, r, l2_first);
+            tma_store_2d_hint(&M.mask_pad, zeros_s, c0, r, l2_first);
+            if (J.want_tt) tma_store_2d_hint(&M.tt_pad, zeros_s, c0, r, l2_first);
+        }
+    }
+    if (t1 > t0) bulk_commit();
+}
+
 // ---- words -------------------------------------------------------------------------------------------------
 // One warp per chunk, no block-wide synchronisation: lane l classifies granule 30c - 1 + l of chunk c, so lanes 1..30 own
 // their granules' words while lane 0 (the granule before) and lane 31 (the granule after) only supply what the neighbours
@@ -132,10 +173,23 @@ struct FlatWarpSmem {
     uint16_t wl[1024];             // words: position in the classified window | length << 10
 };
 template <int MINB>
-__global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, FlatSide S, int insert_ok) {
+__global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, FlatSide S, int insert_ok, PadJob J, const __grid_constant__ TmaPlanes M) {
     __shared__ __align__(16) FlatWarpSmem s_warp[FW_WARPS];
+    extern __shared__ __align__(1024) uint8_t pad_smem[];                   // J.on: [D x PB] pad ids, [D x PB] zero bytes
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     FlatWarpSmem& sm = s_warp[wib];
+    uint32_t pad_s = 0, zeros_s = 0; uint64_t l2_first = 0;
+    if (J.on) {
+        const uint4 pad4 = make_uint4((uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id);
+        uint4* cp = reinterpret_cast<uint4*>(pad_smem);
+        const int n_pad = (int)(r128((size_t)J.D * J.PB * 4) >> 4), n_all = (int)(tma_const_bytes(J.D, J.PB) >> 4);
+        for (int i = tid; i < n_all; i += blockDim.x) cp[i] = i < n_pad ? pad4 : make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+        pad_s = (uint32_t)__cvta_generic_to_shared(pad_smem);
+        zeros_s = pad_s + (uint32_t)r128((size_t)J.D * J.PB * 4);
+        l2_first = l2_policy_evict_first();
+    }
     const int64_t o0 = S.off[0];
     const int64_t P0 = o0 & ~(int64_t)15;
     const uint8_t* __restrict__ tb = S.bytes + P0;
@@ -171,6 +225,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
         reinterpret_cast<uint4*>(text)[lane * 2 + 1] = v1;
         if (lane == 31) reinterpret_cast<uint4*>(text)[64] = v2;
         load_chunk(c + n_warps);                                              // next chunk's text: in flight during this chunk's work
+        if (J.on && lane == 0) flat_pad_tiles(J, M, c, S.nB, pad_s, zeros_s, l2_first);   // this chunk's share of the pad columns
 
         // whitespace bits of my bytes; bytes outside [lo, hi) are not text.  Usual text: a byte is whitespace iff it is
         // <= 0x20 (exact set only when a control character is around); a lead of a multi-byte whitespace (C2, E1..E3) is
@@ -300,6 +355,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
             wtok[i] = val;
         }
     }
+    if (J.on && lane == 0) bulk_wait<0>();      // the constant buffer must outlive the tensor stores that read it
+    __syncwarp();
 }
 
 // after k_bpe_pending: every pending word has its tokens now
@@ -391,21 +448,6 @@ __device__ __forceinline__ int32_t flat_side_tokens(const DevTables& T, const Wo
     return pos;
 }
 
-__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_addr), "r"(c0), "r"(c1) : "memory");
-}
-// the same with an L2 eviction policy: the planes are written once and never read here, they must not push the word
-// arrays (read right after they were written) out of L2
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1, uint64_t policy) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(m), "r"(smem_addr), "r"(c0), "r"(c1), "l"(policy)
-                 : "memory");
-}
-
 // Rows.  The staged ("real") columns 0..KR-1 of a row are computed four positions per lane and stored straight from
 // registers (16-byte streaming stores); the pad columns KR..W-1 -- most of the bytes -- are written by the TMA unit from
 // a block-wide constant buffer, two tensor stores per tile of D rows, with nothing to wait for.
@@ -441,8 +483,10 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
     const uint32_t n_warps = gridDim.x * (uint32_t)wpb;
     uint32_t tok_total = 0;
     const uint64_t l2_first = l2_policy_evict_first();
-    // document offsets of my row in the next tile, loaded one tile ahead (they head the tile's chain of dependent loads)
+    // Two loads head a tile's chain of dependent loads: the document offsets of my row, then the start bits / prefix of the
+    // two granules they point into.  Both are issued ahead: the offsets two tiles ahead, the rank data one tile ahead.
     int64_t pre[2][2] = {{0, 0}, {0, 0}};
+    uint32_t nq[2][2] = {{0, 0}, {0, 0}}, ntp[2][2] = {{0, 0}, {0, 0}}, nst[2][2] = {{0, 0}, {0, 0}};
     auto prefetch_offsets = [&](uint32_t tile) {
         if (tile >= n_tiles) return;
         const int64_t r = (int64_t)tile * D + lane;
@@ -451,13 +495,40 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
             if (pair) { pre[1][0] = A.b.off[r]; pre[1][1] = A.b.off[r + 1]; }
         }
     };
+    auto prefetch_ranks = [&](uint32_t tile) {          // from the offsets in `pre` (which belong to this tile)
+        if (tile >= n_tiles) return;
+        const int64_t r = (int64_t)tile * D + lane;
+        if (lane < D && r < A.n_rows) {
+#pragma unroll
+            for (int s = 0; s < (PAIR ? 2 : 1); s++) {
+                const FlatSide& S = s ? A.b : A.a;
+                const int64_t P0 = s ? P0b : P0a;
+                const uint32_t qmax = S.nB * (uint32_t)FC_BYTES - 64u;      // (offsets beyond the stated text were reported by k_flat_doc_starts)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t q = (uint32_t)min((uint64_t)(pre[s][e] - P0), (uint64_t)qmax);
+                    nq[s][e] = q;
+                    ntp[s][e] = S.tpref[q >> 5];
+                    nst[s][e] = S.st[q >> 5];
+                }
+            }
+        }
+    };
     auto mask_word = [](int32_t c) -> uint32_t { return c >= 4 ? 0x01010101u : (c <= 0 ? 0u : (0x01010101u & ((1u << (8 * c)) - 1))); };
-    prefetch_offsets(blockIdx.x * (uint32_t)wpb + wib);
+    {
+        const uint32_t t0 = blockIdx.x * (uint32_t)wpb + wib;
+        prefetch_offsets(t0);
+        prefetch_ranks(t0);
+        prefetch_offsets(t0 + n_warps);
+    }
     for (uint32_t tile = blockIdx.x * (uint32_t)wpb + wib; tile < n_tiles; tile += n_warps) {
         const int64_t r0 = (int64_t)tile * D;
         const int nd = (int)min((int64_t)D, A.n_rows - r0);
-        const int64_t cur[2][2] = {{pre[0][0], pre[0][1]}, {pre[1][0], pre[1][1]}};
-        prefetch_offsets(tile + n_warps);
+        const uint32_t cq[2][2] = {{nq[0][0], nq[0][1]}, {nq[1][0], nq[1][1]}};
+        const uint32_t ctp[2][2] = {{ntp[0][0], ntp[0][1]}, {ntp[1][0], ntp[1][1]}};
+        const uint32_t cst[2][2] = {{nst[0][0], nst[0][1]}, {nst[1][0], nst[1][1]}};
+        prefetch_ranks(tile + n_warps);
+        prefetch_offsets(tile + 2 * n_warps);
         // ---- the pad columns of the tile: nothing to compute (rows that turn out longer are redone as a whole later)
         if (PB && lane == 0) {
             const int32_t r = (int32_t)r0;
@@ -474,11 +545,9 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
             uint32_t nws[2] = {0u, 0u};
             for (int s = 0; s < (pair ? 2 : 1); s++) {
                 const FlatSide& S = s ? A.b : A.a;
-                const int64_t P0 = s ? P0b : P0a;
-                const uint32_t qmax = S.nB * (uint32_t)FC_BYTES - 64u;      // (offsets beyond the stated text were reported by k_flat_doc_starts)
-                const uint32_t q0 = (uint32_t)min((uint64_t)(cur[s][0] - P0), (uint64_t)qmax), q1 = (uint32_t)min((uint64_t)(cur[s][1] - P0), (uint64_t)qmax);
-                uint32_t b0, b1;
-                const uint32_t rl0 = flat_rank(S, q0, &b0), rl1 = flat_rank(S, q1, &b1);
+                const uint32_t q0 = cq[s][0], q1 = cq[s][1];
+                const uint32_t b0 = q0 / (uint32_t)FC_BYTES, b1 = q1 / (uint32_t)FC_BYTES;
+                const uint32_t rl0 = ctp[s][0] + __popc(cst[s][0] & ((1u << (q0 & 31)) - 1u)), rl1 = ctp[s][1] + __popc(cst[s][1] & ((1u << (q1 & 31)) - 1u));
                 uint32_t nw, avail;
                 if (b0 == b1) { nw = rl1 - rl0; avail = nw; }
                 else {

@@ -94,10 +94,11 @@ struct genztok {
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
     int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
-    int64_t flat_rows = 8;               // rows per warp tile of k_flat_rows
+    int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t cache_slots_log2 = 0;        // EXPERIMENT: fixed word-cache size (no worst-case guarantee)
+    int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
-    int64_t rows_minb = 4, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
+    int64_t rows_minb = 5, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
     int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
     int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
@@ -440,17 +441,37 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 CU(cudaMemsetAsync(S.dsb, 0, ((size_t)S.nB * FC_OWN + 2) * 4, st));
                 { LaunchScope ls(h, d, "k_flat_doc_starts"); k_flat_doc_starts<<<(unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->C, S); }
             }
+            // the pad columns are written by the first k_flat_words launch on the side (tensor stores of [32 x PB] boxes)
+            TmaPlanes Mp;
+            PadJob J{};
+            if (M.PB > 0 && !h->no_side_pads) {
+                RowArgs Ap = A;
+                Ap.D = 32;
+                const int64_t keep_kr = h->force_kr;
+                h->force_kr = M.KR;                                   // the same split of the columns as k_flat_rows uses
+                const bool okp = setup_tma(h, d, Ap, bytes, &Mp, sizeof(FlatTile)) && Mp.KR == M.KR && Mp.PB == M.PB;
+                h->force_kr = keep_kr;
+                if (okp) {
+                    J.on = 1; J.n_tiles = (int32_t)((n + 31) / 32); J.W = W; J.D = 32; J.KR = Mp.KR; J.PB = Mp.PB;
+                    J.want_tt = (F.has_pair && F.tt) ? 1 : 0; J.pad_id = d->T.pad;
+                }
+            }
+            static const TmaPlanes no_planes{};
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
                 LaunchScope ls(h, d, "k_flat_words");
+                const bool pads = J.on != 0;                          // every launch takes its share of the pad tiles
+                PadJob Js = J;
+                if (b) { const int32_t half = J.n_tiles / 2; Js.tile0 = s ? half : 0; Js.n_tiles = s ? J.n_tiles - half : half; }
+                const size_t dsm = pads ? tma_const_bytes(J.D, J.PB) : 0;
                 const unsigned per_sm = (unsigned)std::max<int64_t>(1, h->words_minb) * (8 / FW_WARPS);
                 const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)S.nB + FW_WARPS - 1) / FW_WARPS, (uint64_t)d->sm_count * per_sm);
-                switch (h->words_minb) {
-                    case 5: k_flat_words<5><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
-                    case 6: k_flat_words<6><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
-                    default: k_flat_words<4><<<grid, FW_WARPS * 32, 0, st>>>(d->T, d->C, S, 1); break;
-                }
+                auto wk = h->words_minb == 6 ? k_flat_words<6> : (h->words_minb == 5 ? k_flat_words<5> : k_flat_words<4>);
+                if (dsm) CU(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                wk<<<grid, FW_WARPS * 32, dsm, st>>>(d->T, d->C, S, 1, Js, pads ? Mp : no_planes);
+                CU(cudaGetLastError());
             }
+            if (J.on) M.PB = 0;                                       // k_flat_rows: real columns only
             CU(cudaGetLastError());
             rc = launch_bpe(h, d, st);
             if (rc) return rc;
@@ -463,7 +484,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * (r128(sizeof(FlatTile)) + r128((size_t)M.KR * 4));
                 (void)tt;
                 auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 5 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
-                                       : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>));
+                                       : (h->rows_minb == 8 ? k_flat_rows<8, false> : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>)));
                 if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 1;
                 CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -653,6 +674,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->flat_rows = value;
     } else if (n == "cache_slots_log2") {
         h->cache_slots_log2 = value;
+    } else if (n == "no_side_pads") {
+        h->no_side_pads = value;
     } else if (n == "rows_grid") {
         h->rows_grid = value;
     } else if (n == "rows_minb") {
