@@ -172,7 +172,7 @@ struct FlatWarpSmem {
     uint8_t text[1024 + 16];       // the 32 classified granules and 16 bytes more (key gathers)
     uint16_t wl[1024];             // words: position in the classified window | length << 10
 };
-template <int MINB>
+template <int MINB, int ILP>
 __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, FlatSide S, int insert_ok, PadJob J, const __grid_constant__ TmaPlanes M) {
     __shared__ __align__(16) FlatWarpSmem s_warp[FW_WARPS];
     extern __shared__ __align__(1024) uint8_t pad_smem[];                   // J.on: [D x PB] pad ids, [D x PB] zero bytes
@@ -324,25 +324,32 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
         // one word per lane: its key from the staged text (aligned 16-byte pieces + funnel shifts), one probe of the word's
         // home slot -- the second half of the slot only for words longer than 8 bytes
         uint32_t* const wtok = S.wtok + ((size_t)c << FC_SHIFT);
-        for (uint32_t i = lane; i < total; i += 32) {
+        // (two words per lane and step: both probes are in flight before either is examined)
+        auto prep = [&](uint32_t i, uint32_t& p, uint32_t& len, uint64_t& k0, uint64_t& k1, uint64_t& k2, uint32_t& h, uint4& a, uint4& b) {
+            // returns true when the word takes the fast path (key in k0..k2, slot halves being loaded into a / b)
+            a = make_uint4(0u, 0u, 0u, 0u); b = a; p = 0; len = 0; k0 = k1 = k2 = 0; h = 0;
+            if (i >= total) return false;
             const uint32_t e = sm.wl[i];
-            const uint32_t p = e & 1023u, len = e >> 10;
+            p = e & 1023u; len = e >> 10;
+            if (len == 0 || len > KEY_INLINE) return false;
+            const uint32_t a16 = p & ~15u;
+            const int s16 = (int)(p & 15u);
+            const uint4 x0 = *reinterpret_cast<const uint4*>(text + a16);
+            const uint4 x1 = *reinterpret_cast<const uint4*>(text + a16 + 16);
+            uint2 x2 = make_uint2(0u, 0u);
+            if (s16 + (int)len > 32) x2 = *reinterpret_cast<const uint2*>(text + a16 + 32);
+            key_from_pieces40_nomask(x0, x1, x2, s16, &k0, &k1, &k2);
+            key_mask24(len, &k0, &k1, &k2);
+            h = hash_key24(k0, k1, k2, len);
+            const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
+            a = slot[0];
+            if (len > 8) b = slot[1];          // (equal lengths <= 8: the rest of both keys is zero)
+            return true;
+        };
+        auto done = [&](uint32_t i, bool fast, uint32_t p, uint32_t len, uint64_t k0, uint64_t k1, uint64_t k2, uint32_t h, const uint4& a, const uint4& b) {
+            if (i >= total) return;
             uint32_t val;
-            if (len != 0 && len <= KEY_INLINE) {
-                const uint32_t a16 = p & ~15u;
-                const int s16 = (int)(p & 15u);
-                const uint4 x0 = *reinterpret_cast<const uint4*>(text + a16);
-                const uint4 x1 = *reinterpret_cast<const uint4*>(text + a16 + 16);
-                uint2 x2 = make_uint2(0u, 0u);
-                if (s16 + (int)len > 32) x2 = *reinterpret_cast<const uint2*>(text + a16 + 32);
-                uint64_t k0, k1, k2;
-                key_from_pieces40_nomask(x0, x1, x2, s16, &k0, &k1, &k2);
-                key_mask24(len, &k0, &k1, &k2);
-                const uint32_t h = hash_key24(k0, k1, k2, len);
-                const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
-                const uint4 a = slot[0];
-                uint4 b = make_uint4(0u, 0u, 0u, 0u);
-                if (len > 8) b = slot[1];          // (equal lengths <= 8: the rest of both keys is zero)
+            if (fast) {
                 const uint64_t s0 = ((uint64_t)a.w << 32) | a.z, s1 = ((uint64_t)b.y << 32) | b.x, s2 = ((uint64_t)b.w << 32) | b.z;
                 val = a.y;
                 if (!((a.x == len) & (s0 == k0) & (s1 == k1) & (s2 == k2))) val = cache_find_or_insert(C, tb + wq + p, len, k0, k1, k2, h, insert_ok != 0);
@@ -353,6 +360,22 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
                 else atomicAdd(&C.ctr[C_ERR], 1ULL);
             }
             wtok[i] = val;
+        };
+        if (ILP == 2) {
+            for (uint32_t base = 0; base < total; base += 64) {
+                const uint32_t i1 = base + lane, i2 = i1 + 32;
+                uint32_t p1, l1, h1, p2, l2, h2; uint64_t ka0, ka1, ka2, kb0, kb1, kb2; uint4 a1, b1, a2, b2;
+                const bool f1 = prep(i1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
+                const bool f2 = prep(i2, p2, l2, kb0, kb1, kb2, h2, a2, b2);
+                done(i1, f1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
+                done(i2, f2, p2, l2, kb0, kb1, kb2, h2, a2, b2);
+            }
+        } else {
+            for (uint32_t i = lane; i < total; i += 32) {
+                uint32_t p1, l1, h1; uint64_t ka0, ka1, ka2; uint4 a1, b1;
+                const bool f1 = prep(i, p1, l1, ka0, ka1, ka2, h1, a1, b1);
+                done(i, f1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
+            }
         }
     }
     if (J.on && lane == 0) bulk_wait<0>();      // the constant buffer must outlive the tensor stores that read it

@@ -337,14 +337,15 @@ bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes
 // Can the fixed-layout kernel stage one row of W ids (one document per tile, one warp per block)?
 bool fixed_fits(const DeviceCtx* d, int32_t W) { return sizeof(TileSmem) + row_stage_bytes(d, W, 1) <= d->smem_optin; }
 
-int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force) {
+int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes, int force, uint32_t* z0 = nullptr, uint64_t n0 = 0, uint32_t* z1 = nullptr,
+                 uint64_t n1 = 0) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
         k_cache_guard<<<1, 1, 0, st>>>(d->C, h->cache_slots_log2 > 0 ? 1024ull : (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
-        k_cache_clear<<<d->sm_count * 4, 256, 0, st>>>(d->C);
+        k_cache_clear<<<d->sm_count * 4, 256, 0, st>>>(d->C, z0, n0, z1, n1);
     }
     CU(cudaGetLastError());
     return GENZTOK_OK;
@@ -405,8 +406,6 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     if (n <= 0) return GENZTOK_OK;
     CU(d->redo.ensure((size_t)n * 4));
     CU(d->fix.ensure((size_t)n * 4));
-    rc = launch_guard(h, d, st, bytes + 16, 0);
-    if (rc) return rc;
     RowArgs A{};
     A.a = a;
     if (b) A.b = *b;
@@ -436,9 +435,11 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             }
             F.has_pair = b != nullptr; F.n_rows = n; F.W = W; F.D = Af.D; F.ids = A.ids; F.mask = A.mask; F.tt = A.tt;
             F.row_len = A.row_len; F.seq_len = A.seq_len; F.status = A.status; F.redo_list = A.redo_list; F.fix_list = A.fix_list; F.eos_i8 = A.eos_i8;
+            // cache guard / clear; the document-start bitmaps are zeroed by the same launch
+            rc = launch_guard(h, d, st, bytes + 16, 0, F.a.dsb, (uint64_t)F.a.nB * FC_OWN + 2, b ? F.b.dsb : nullptr, b ? (uint64_t)F.b.nB * FC_OWN + 2 : 0);
+            if (rc) return rc;
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
-                CU(cudaMemsetAsync(S.dsb, 0, ((size_t)S.nB * FC_OWN + 2) * 4, st));
                 { LaunchScope ls(h, d, "k_flat_doc_starts"); k_flat_doc_starts<<<(unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->C, S); }
             }
             // the pad columns are written by the first k_flat_words launch on the side (tensor stores of [32 x PB] boxes)
@@ -464,9 +465,10 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 PadJob Js = J;
                 if (b) { const int32_t half = J.n_tiles / 2; Js.tile0 = s ? half : 0; Js.n_tiles = s ? J.n_tiles - half : half; }
                 const size_t dsm = pads ? tma_const_bytes(J.D, J.PB) : 0;
-                const unsigned per_sm = (unsigned)std::max<int64_t>(1, h->words_minb) * (8 / FW_WARPS);
+                auto wk = h->words_minb == 3 ? k_flat_words<3, 2> : (h->words_minb == 14 ? k_flat_words<4, 2> : (h->words_minb == 5 ? k_flat_words<5, 1> : k_flat_words<4, 1>));
+                const int64_t wmb = h->words_minb == 14 ? 4 : h->words_minb;
+                const unsigned per_sm = (unsigned)std::max<int64_t>(1, wmb) * (8 / FW_WARPS);
                 const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)S.nB + FW_WARPS - 1) / FW_WARPS, (uint64_t)d->sm_count * per_sm);
-                auto wk = h->words_minb == 6 ? k_flat_words<6> : (h->words_minb == 5 ? k_flat_words<5> : k_flat_words<4>);
                 if (dsm) CU(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
                 wk<<<grid, FW_WARPS * 32, dsm, st>>>(d->T, d->C, S, 1, Js, pads ? Mp : no_planes);
                 CU(cudaGetLastError());
@@ -477,7 +479,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             if (rc) return rc;
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
-                LaunchScope ls(h, d, "k_flat_fix"); k_flat_fix<<<d->sm_count * 4, 256, 0, st>>>(d->C, S);
+                LaunchScope ls(h, d, "k_flat_fix"); k_flat_fix<<<d->sm_count * 2, 256, 0, st>>>(d->C, S);
             }
             {
                 const bool tt = F.has_pair && F.tt;
@@ -499,6 +501,8 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         }
     }
     if (!flat) {
+        rc = launch_guard(h, d, st, bytes + 16, 0);
+        if (rc) return rc;
         const bool tma = setup_tma(h, d, A, bytes, &M);
         rc = launch_rows<MODE_FIXED>(h, d, A, st, tma ? "k_rows_fixed_tma" : "k_rows_fixed", n, tma ? &M : nullptr);
         if (rc) return rc;

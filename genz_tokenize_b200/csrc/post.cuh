@@ -334,12 +334,16 @@ __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsign
     if (reset) { c[C_SLOTS] = 0; c[C_KEYS] = 0; c[C_TOKS] = 0; }
     c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0;
 }
-__global__ void k_cache_clear(WordCache C) {
+// ... and two optional word arrays to zero on the way (the document-start bitmaps of the byte-parallel pipeline)
+__global__ void k_cache_clear(WordCache C, uint32_t* z0, uint64_t n0, uint32_t* z1, uint64_t n1) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = tid; i < n0; i += nth) z0[i] = 0u;
+    for (uint64_t i = tid; i < n1; i += nth) z1[i] = 0u;
     if (!C.ctr[C_RESET]) return;
     uint4* p = reinterpret_cast<uint4*>(C.slots);
     const uint64_t n = ((uint64_t)C.mask + 1) * 2;
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = z;
+    for (uint64_t i = tid; i < n; i += nth) p[i] = z;
 }
 __global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; C.ctr[C_FLATFIX_A] = 0; C.ctr[C_FLATFIX_B] = 0; }
 
