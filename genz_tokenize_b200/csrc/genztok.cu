@@ -95,7 +95,6 @@ struct genztok {
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
     int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
-    int64_t cache_slots_log2 = 0;        // EXPERIMENT: fixed word-cache size (no worst-case guarantee)
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
     int64_t rows_minb = 5, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
@@ -208,7 +207,7 @@ uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p
 int ensure_cache(genztok_t* h, DeviceCtx* d) {
     if (d->cache_ready) return GENZTOK_OK;
     const uint64_t B = (uint64_t)h->max_chunk_bytes;
-    const uint64_t slots = h->cache_slots_log2 > 0 ? (1ull << h->cache_slots_log2) : std::max<uint64_t>(next_pow2(B), 1024);
+    const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
     CU(d->slots.ensure(slots * sizeof(Slot)));
     CU(d->key_arena.ensure(B + 64));
     CU(d->tok_arena.ensure((2 * B + 64) * 4));
@@ -341,7 +340,7 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
                  uint64_t n1 = 0) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
-        k_cache_guard<<<1, 1, 0, st>>>(d->C, h->cache_slots_log2 > 0 ? 1024ull : (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
+        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
@@ -676,8 +675,6 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "flat_rows") {
         if (value < 1 || value > 32) return fail(h, GENZTOK_E_INVALID, "flat_rows must be in 1..32");
         h->flat_rows = value;
-    } else if (n == "cache_slots_log2") {
-        h->cache_slots_log2 = value;
     } else if (n == "no_side_pads") {
         h->no_side_pads = value;
     } else if (n == "rows_grid") {
