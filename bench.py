@@ -321,7 +321,10 @@ def main():
     alg_bytes = in_bytes + 8 * (n + 1) + n * MAX_LEN * (4 + 1)          # the whole path, per GPU per step
     # algorithmic bytes of the dominant kernel alone: k_flat_rows turns offsets into planes (it never reads the text);
     # k_flat_words reads the text; the fused k_rows_fixed* kernels do the whole path in one launch
-    kernel_alg = {"k_flat_rows": 8 * (n + 1) + n * MAX_LEN * (4 + 1), "k_flat_words": in_bytes}
+    # (the pipeline stages KR columns per row -- genztok.cu setup_tma: bytes/rows/3 + 12 rounded up to 16, at least 32 -- and
+    #  k_flat_words writes the other max_len - KR pad columns of both planes on the side)
+    kr = min(MAX_LEN, max(32, (in_bytes // n // 3 + 12 + 15) // 16 * 16))
+    kernel_alg = {"k_flat_rows": 8 * (n + 1) + n * kr * (4 + 1), "k_flat_words": in_bytes + n * (MAX_LEN - kr) * (4 + 1)}
     dom_alg = kernel_alg.get(dom_name, alg_bytes)
     achieved = dom_alg / (k_ms * 1e-3) / 1e9
     traffic, traffic_all = None, None
