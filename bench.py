@@ -120,7 +120,8 @@ def run_reference(args, rank, world):
         return
     from genz_tokenize_b200 import workload
     from oracle.oracle import Oracle
-    threads = Oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm uses every core of the host regardless
+    threads = max(Oracle.max_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     n_sample = N_DOCS
     tb, to = workload.generate(SEED, n_sample, 3, 13, 0.0)
     for _ in range(max(args.warmup, 0)):
@@ -366,11 +367,11 @@ def main():
     }
     if extra is not None:
         line["extra"] = extra
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:            # the CPU baseline is reported at N=1 only
         threads = 0
         try:
             from oracle.oracle import Oracle
-            threads = Oracle.max_threads()
+            threads = max(Oracle.max_threads(), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
             n1 = min(n, 1 << 19)
             r1, _, dt1 = oracle_rate(tb, to, n1, 1)
             reps = 12
