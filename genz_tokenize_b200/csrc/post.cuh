@@ -233,22 +233,47 @@ static const int DEC_MAXFORM = 32;     // forms longer than this go straight to 
 // Pass 1 (WRITE == false): bytes per row.  Pass 2: gather the forms into a per-warp shared-memory staging buffer
 // and write the text with aligned 16-byte stores (edges bytewise: neighbouring rows belong to other warps).
 template <bool WRITE>
-__global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
+__global__ void __launch_bounds__(256, WRITE ? 4 : 6) k_decode(DevTables T, DecArgs A) {
     __shared__ __align__(16) uint8_t stage[WRITE ? 8 : 1][WRITE ? DEC_CAP + 16 : 16];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     uint8_t* ob = stage[WRITE ? wib : 0];
+    // The padding of fixed-width rows decodes to one short form repeated: sixteen-byte units of that periodic text, one per
+    // phase, are kept per warp so that a run of pad ids is written as whole units instead of byte by byte.
+    __shared__ __align__(16) uint8_t padtab[WRITE ? 8 : 1][WRITE ? 8 : 1][16];
+    uint32_t padL = 0; uint64_t padP = 0;
+    if (WRITE) {
+        uint32_t off, len;
+        dec_form(T, T.pad, false, &off, &len);
+        if (len >= 1 && len <= 8) {
+            padL = len;
+            padP = *reinterpret_cast<const uint64_t*>(T.form_blob + off);
+            if (lane < (int)len) {
+                int ph = lane;
+                for (int k = 0; k < 16; k++) { padtab[wib][lane][k] = (uint8_t)(padP >> (8 * ph)); ph = ph + 1 == (int)len ? 0 : ph + 1; }
+            }
+        }
+        __syncwarp();
+    }
     for (uint64_t r = warp; r < (uint64_t)A.n_rows; r += nwarps) {
         const int64_t start = A.ids_off ? A.ids_off[r] : (int64_t)r * A.width;
         const int64_t n = A.ids_off ? A.ids_off[r + 1] - start : A.width;
         const int32_t* ids = A.ids + start;
         if (!WRITE) {
             int64_t run = 0;
-            for (int64_t base = 0; base < n; base += 32) {
-                const int64_t i = base + lane;
-                uint32_t off = 0, len = 0;
-                if (i < n) dec_form(T, ids[i], i == n - 1, &off, &len);
-                run += __reduce_add_sync(FULL_MASK, len);
+            for (int64_t base = 0; base < n; base += 256) {              // eight batches of ids in flight
+                int32_t idv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int64_t i = base + 32 * k + lane; idv[k] = i < n ? ids[i] : 0; }
+                uint32_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int64_t i = base + 32 * k + lane;
+                    uint32_t off = 0, len = 0;
+                    if (i < n) dec_form(T, idv[k], i == n - 1, &off, &len);
+                    sum += len;
+                }
+                run += __reduce_add_sync(FULL_MASK, sum);
             }
             if (lane == 0) A.out_len[r] = run;
             continue;
@@ -279,39 +304,78 @@ __global__ void __launch_bounds__(256) k_decode(DevTables T, DecArgs A) {
             gbase += nfull; cur = rem; lead = 0;
             __syncwarp();
         };
-        for (int64_t base = 0; base < n; base += 32) {
-            const int64_t i = base + lane;
-            uint32_t off = 0, len = 0;
-            if (i < n) dec_form(T, ids[i], i == n - 1, &off, &len);
-            uint32_t incl = len;
+        for (int64_t base0 = 0; base0 < n; base0 += 256) {
+            int32_t idv[8];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-            const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
-            const bool big = __any_sync(FULL_MASK, len > (uint32_t)DEC_MAXFORM);
-            const uint8_t* src = T.form_blob + off;
-            if (!big) {
-                if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
-                uint8_t* d = ob + cur + (incl - len);
-                for (uint32_t k0 = 0; k0 < len; k0 += 8) {              // forms are 8-byte aligned in the blob: one load per 8 bytes
-                    uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);
-                    const uint32_t nb = len - k0 < 8u ? len - k0 : 8u;
+            for (int k = 0; k < 8; k++) { const int64_t i = base0 + 32 * k + lane; idv[k] = i < n ? ids[i] : 0; }
+            uint32_t upad = 0;                                  // batches of this group that are all padding
 #pragma unroll
-                    for (uint32_t k = 0; k < 8; k++) if (k < nb) d[k0 + k] = (uint8_t)(v >> (8 * k));
+            for (int k = 0; k < 8; k++) {
+                const int64_t i = base0 + 32 * k + lane;
+                if (__all_sync(FULL_MASK, idv[k] == T.pad && i < n - 1)) upad |= 1u << k;
+            }
+#pragma unroll 1
+            for (int kb = 0; kb < 8; kb++) {
+                const int64_t base = base0 + 32 * kb;
+                if (base >= n) break;
+                // a run of batches that hold nothing but pad ids (and not the row's last id): whole units of the periodic text
+                if (padL && (upad >> kb) & 1u) {
+                    int rl = 1;
+                    while (kb + rl < 8 && ((upad >> (kb + rl)) & 1u)) rl++;
+                    const int L = (int)padL, total = 32 * L * rl;
+                    if (cur + total > DEC_CAP) flush(cur & ~15, false);
+                    const int s0 = cur, s1 = cur + total;
+                    const int a0 = (s0 + 15) & ~15, a1 = s1 & ~15;                       // whole 16-byte units inside [s0, s1)
+                    {
+                        int ph = (a0 - s0 + lane * 16) % L;
+                        const int step = 512 % L;
+                        for (int u = a0 + lane * 16; u < a1; u += 512) {
+                            *reinterpret_cast<uint4*>(ob + u) = *reinterpret_cast<const uint4*>(padtab[wib][ph]);
+                            ph += step; if (ph >= L) ph -= L;
+                        }
+                    }
+                    if (s0 + lane < a0) ob[s0 + lane] = (uint8_t)(padP >> (8 * (lane % L)));
+                    if (a1 + lane < s1) ob[a1 + lane] = (uint8_t)(padP >> (8 * ((a1 - s0 + lane) % L)));
+                    cur += total;
+                    kb += rl - 1;
+                    continue;
                 }
-                cur += (int)tot;
-            } else {                                        // rare: a very long vocab entry -> write this batch directly
-                if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */
+                const int64_t i = base + lane;
+                int32_t myid = idv[0];
+#pragma unroll
+                for (int k = 1; k < 8; k++) if (kb == k) myid = idv[k];
+                uint32_t off = 0, len = 0;
+                if (i < n) dec_form(T, myid, i == n - 1, &off, &len);
+                const uint8_t* src = T.form_blob + off;
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+                const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+                const bool big = __any_sync(FULL_MASK, len > (uint32_t)DEC_MAXFORM);
+                if (!big) {
+                    if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
+                    uint8_t* d = ob + cur + (incl - len);
+                    for (uint32_t k0 = 0; k0 < len; k0 += 8) {              // forms are 8-byte aligned in the blob: one load per 8 bytes
+                        uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);
+                        const uint32_t nb = len - k0 < 8u ? len - k0 : 8u;
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; k++) if (k < nb) d[k0 + k] = (uint8_t)(v >> (8 * k));
+                    }
+                    cur += (int)tot;
+                } else {                                        // rare: a very long vocab entry -> write this batch directly
+                    if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */
+                        __syncwarp();
+                        for (int k = lead + lane; k < cur; k += 32) gbase[k] = ob[k];
+                    }
+                    uint8_t* d = gbase + cur + (incl - len);
+                    for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+                    // restart the staging buffer at the new position
+                    const int64_t gpos = (gbase - A.out) + cur + (int64_t)tot;
+                    gbase = A.out + (gpos & ~(int64_t)15);
+                    lead = (int)(gpos & 15);
+                    cur = lead;
                     __syncwarp();
-                    for (int k = lead + lane; k < cur; k += 32) gbase[k] = ob[k];
                 }
-                uint8_t* d = gbase + cur + (incl - len);
-                for (uint32_t k = 0; k < len; k++) d[k] = src[k];
-                // restart the staging buffer at the new position
-                const int64_t gpos = (gbase - A.out) + cur + (int64_t)tot;
-                gbase = A.out + (gpos & ~(int64_t)15);
-                lead = (int)(gpos & 15);
-                cur = lead;
-                __syncwarp();
             }
         }
         flush(0, true);

@@ -1,0 +1,35 @@
+"""Decode of padded rows on one GPU: per-kernel times (library-side CUDA events)."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genz_tokenize_b200 import Tokenize, workload
+n = 1 << 20
+dev = torch.device("cuda:0")
+tok = Tokenize(devices=[0])
+for kv in os.environ.get("GENZTOK_OPTIONS", "").split(","):
+    if "=" in kv:
+        tok.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+tb, to = workload.generate(1234, n, 3, 13, 0.0)
+pad16 = lambda a: torch.from_numpy(np.concatenate([a, np.zeros((-len(a)) % 16 + 16, dtype=np.uint8)])).to(dev)
+d_t, d_to = pad16(tb), torch.from_numpy(to).to(dev)
+for W in (128, 256):
+    out = {"input_ids": torch.empty((n, W), dtype=torch.int32, device=dev), "attention_mask": torch.empty((n, W), dtype=torch.uint8, device=dev),
+           "row_len": torch.empty((n,), dtype=torch.int32, device=dev)}
+    tok.encode_device(d_t, d_to, max_len=W, out=out, text_bytes=len(tb))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        txt, off = tok.decode_device(out["input_ids"])
+    torch.cuda.synchronize()
+    tok.set_profiling(True); tok.profile_report(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in ev:
+        a.record(); txt, off = tok.decode_device(out["input_ids"]); b.record()
+    torch.cuda.synchronize()
+    prof = tok.profile_report(reset=True)
+    tok.set_profiling(False)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / 5
+    alg = 4 * n * W + int(txt.numel()) + 16 * n
+    print("W=%d ms %.3f alg GB/s %.0f text MB %.0f" % (W, ms, alg / ms / 1e6, txt.numel() / 1e6), {k: round(v["ms"] / 5, 4) for k, v in prof.items()})
+    import hashlib
+    print("  sha", hashlib.sha256(txt[:1 << 24].cpu().numpy().tobytes()).hexdigest()[:16], int(off[-1].item()))
