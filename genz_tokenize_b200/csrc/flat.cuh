@@ -132,6 +132,18 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// The slots of the frequent words are read again and again while hundreds of MB of planes stream through L2: the probes ask
+// L2 to evict those lines last, so that a batch of probes does not wait for the one that had to go to DRAM.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_keep128(const uint4* p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
 __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(m), "r"(smem_addr), "r"(c0), "r"(c1), "l"(policy)
                  : "memory");
@@ -179,6 +191,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     FlatWarpSmem& sm = s_warp[wib];
     uint32_t pad_s = 0, zeros_s = 0; uint64_t l2_first = 0;
+    const uint64_t l2_last = l2_policy_evict_last();
     if (J.on) {
         const uint4 pad4 = make_uint4((uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id);
         uint4* cp = reinterpret_cast<uint4*>(pad_smem);
@@ -342,8 +355,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
             key_mask24(len, &k0, &k1, &k2);
             h = hash_key24(k0, k1, k2, len);
             const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
-            a = slot[0];
-            if (len > 8) b = slot[1];          // (equal lengths <= 8: the rest of both keys is zero)
+            a = ld_keep128(slot, l2_last);
+            if (len > 8) b = ld_keep128(slot + 1, l2_last);          // (equal lengths <= 8: the rest of both keys is zero)
             return true;
         };
         auto done = [&](uint32_t i, bool fast, uint32_t p, uint32_t len, uint64_t k0, uint64_t k1, uint64_t k2, uint32_t h, const uint4& a, const uint4& b) {
