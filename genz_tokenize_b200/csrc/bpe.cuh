@@ -106,6 +106,7 @@ __device__ __forceinline__ int32_t sym_to_id(const DevTables& T, uint32_t s, boo
 
 // One warp per pending cache slot.
 __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
+    pdl_wait(); pdl_trigger();
     __shared__ uint32_t sm_sym[8][BPE_SMEM_SYMS];
     __shared__ __align__(16) uint8_t sm_key[8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

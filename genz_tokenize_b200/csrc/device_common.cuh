@@ -59,6 +59,11 @@ struct WordCache {
     unsigned long long* ctr;  // Counter[]
 };
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may be scheduled while its
+// predecessor drains; it must not touch the predecessor's results before pdl_wait().  pdl_trigger() lets the successor be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 // A load that is really performed every time it is executed and is served by L2 (L1 may hold a stale copy of

@@ -622,6 +622,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
 // TMA (MODE_FIXED, TokT = int32_t only): the planes are written by tensor stores from a final-form staging area (see TmaPlanes).
 template <int MODE, typename TokT, bool TMA>
 __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A, const __grid_constant__ TmaPlanes M) {
+    pdl_wait(); pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D;

@@ -112,6 +112,7 @@ __device__ __noinline__ void flat_lookahead(const uint8_t* tb, const uint32_t* d
 
 // ---- document starts ---------------------------------------------------------------------------------------
 __global__ void k_flat_doc_starts(WordCache C, FlatSide S) {
+    pdl_wait(); pdl_trigger();
     const int64_t o0 = S.off[0];
     const int64_t P0 = o0 & ~(int64_t)15;
     const int64_t capq = (int64_t)S.nB * FC_BYTES - 64;
@@ -186,6 +187,7 @@ struct FlatWarpSmem {
 };
 template <int MINB, int ILP>
 __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, FlatSide S, int insert_ok, PadJob J, const __grid_constant__ TmaPlanes M) {
+    pdl_wait(); pdl_trigger();
     __shared__ __align__(16) FlatWarpSmem s_warp[FW_WARPS];
     extern __shared__ __align__(1024) uint8_t pad_smem[];                   // J.on: [D x PB] pad ids, [D x PB] zero bytes
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -397,6 +399,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
 
 // after k_bpe_pending: every pending word has its tokens now
 __global__ void k_flat_fix(WordCache C, FlatSide S) {
+    pdl_wait(); pdl_trigger();
     const int64_t o0 = S.off[0];
     const int64_t P0 = o0 & ~(int64_t)15;
     const uint8_t* tb = S.bytes + P0;
@@ -489,6 +492,7 @@ __device__ __forceinline__ int32_t flat_side_tokens(const DevTables& T, const Wo
 // a block-wide constant buffer, two tensor stores per tile of D rows, with nothing to wait for.
 template <int MINB, bool PAIR>
 __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache C, FlatRowsArgs A, const __grid_constant__ TmaPlanes M) {
+    pdl_wait(); pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D, KR = M.KR, PB = M.PB;

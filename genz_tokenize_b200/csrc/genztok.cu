@@ -160,6 +160,19 @@ struct LaunchScope {   // counts the launch and, when profiling, brackets it wit
 };
 thread_local cudaStream_t LaunchScope::cur_stream = nullptr;
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in device_common.cuh): the kernel may be scheduled
+// while its predecessor in the stream drains, which takes most of the launch gap out of chains of short kernels.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 template <class T>
 cudaError_t upload(DeviceCtx* d, const std::vector<T>& v, const T** out) {
     void* p = nullptr;
@@ -266,7 +279,7 @@ int launch_rows_t(genztok_t* h, DeviceCtx* d, const RowArgs& A, cudaStream_t st,
     if (blocks < 1) blocks = 1;
     static const TmaPlanes no_planes{};
     LaunchScope ls(h, d, name);
-    kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(d->T, d->C, A, TMA ? *M : no_planes);
+    CU(launch_pdl(kern, dim3((unsigned)blocks), dim3(wpb * 32), smem, st, d->T, d->C, A, TMA ? *M : no_planes));
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
@@ -340,11 +353,11 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
                  uint64_t n1 = 0) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
-        k_cache_guard<<<1, 1, 0, st>>>(d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force);
+        CU(launch_pdl(k_cache_guard, dim3(1), dim3(1), 0, st, d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force));
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
-        k_cache_clear<<<d->sm_count * 4, 256, 0, st>>>(d->C, z0, n0, z1, n1);
+        CU(launch_pdl(k_cache_clear, dim3(d->sm_count * 4), dim3(256), 0, st, d->C, z0, n0, z1, n1));
     }
     CU(cudaGetLastError());
     return GENZTOK_OK;
@@ -352,7 +365,7 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
 
 int launch_bpe(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     LaunchScope ls(h, d, "k_bpe_pending");
-    k_bpe_pending<<<d->sm_count * 4, 256, 0, st>>>(d->T, d->C);
+    CU(launch_pdl(k_bpe_pending, dim3(d->sm_count * 4), dim3(256), 0, st, d->T, d->C));
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
@@ -439,7 +452,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             if (rc) return rc;
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
-                { LaunchScope ls(h, d, "k_flat_doc_starts"); k_flat_doc_starts<<<(unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->C, S); }
+                { LaunchScope ls(h, d, "k_flat_doc_starts"); CU(launch_pdl(k_flat_doc_starts, dim3((unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8)), dim3(256), 0, st, d->C, S)); }
             }
             // the pad columns are written by the first k_flat_words launch on the side (tensor stores of [32 x PB] boxes)
             TmaPlanes Mp;
@@ -469,7 +482,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 const unsigned per_sm = (unsigned)std::max<int64_t>(1, wmb) * (8 / FW_WARPS);
                 const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)S.nB + FW_WARPS - 1) / FW_WARPS, (uint64_t)d->sm_count * per_sm);
                 if (dsm) CU(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                wk<<<grid, FW_WARPS * 32, dsm, st>>>(d->T, d->C, S, 1, Js, pads ? Mp : no_planes);
+                CU(launch_pdl(wk, dim3(grid), dim3(FW_WARPS * 32), dsm, st, d->T, d->C, S, 1, Js, pads ? Mp : no_planes));
                 CU(cudaGetLastError());
             }
             if (J.on) M.PB = 0;                                       // k_flat_rows: real columns only
@@ -478,7 +491,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             if (rc) return rc;
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
-                LaunchScope ls(h, d, "k_flat_fix"); k_flat_fix<<<d->sm_count * 2, 256, 0, st>>>(d->C, S);
+                LaunchScope ls(h, d, "k_flat_fix"); CU(launch_pdl(k_flat_fix, dim3(d->sm_count * 2), dim3(256), 0, st, d->C, S));
             }
             {
                 const bool tt = F.has_pair && F.tt;
@@ -494,7 +507,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 if (h->rows_grid > 0) occ = std::min<int>(occ, (int)h->rows_grid);
                 const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)d->sm_count * occ * h->grid_mult));
                 LaunchScope ls(h, d, "k_flat_rows");
-                kern<<<(unsigned)blocks, 256, smem, st>>>(d->T, d->C, F, M);
+                CU(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, d->T, d->C, F, M));
             }
             CU(cudaGetLastError());
         }

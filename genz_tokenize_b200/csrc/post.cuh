@@ -391,6 +391,7 @@ __global__ void k_mask_flat(const int32_t* ids, int64_t n, int32_t pad, uint8_t*
 // ---- word cache housekeeping -------------------------------------------------------------------------
 // Decide whether the cache can take the worst case of the next chunk; if not, schedule a reset.
 __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsigned long long need_keys, unsigned long long need_toks, int force) {
+    pdl_wait(); pdl_trigger();
     unsigned long long* c = C.ctr;
     const unsigned long long cap = (unsigned long long)C.mask + 1;
     const bool reset = force || (c[C_SLOTS] + need_slots) * 2 > cap || c[C_KEYS] + need_keys > C.key_cap || c[C_TOKS] + need_toks > C.tok_cap;
@@ -400,6 +401,7 @@ __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsign
 }
 // ... and two optional word arrays to zero on the way (the document-start bitmaps of the byte-parallel pipeline)
 __global__ void k_cache_clear(WordCache C, uint32_t* z0, uint64_t n0, uint32_t* z1, uint64_t n1) {
+    pdl_wait(); pdl_trigger();
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = tid; i < n0; i += nth) z0[i] = 0u;
     for (uint64_t i = tid; i < n1; i += nth) z1[i] = 0u;
