@@ -457,7 +457,8 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             // the pad columns are written by the first k_flat_words launch on the side (tensor stores of [32 x PB] boxes)
             TmaPlanes Mp;
             PadJob J{};
-            if (M.PB > 0 && !h->no_side_pads) {
+            // (not when the text is tiny next to the planes -- empty documents: a few chunks would have to issue all the boxes)
+            if (M.PB > 0 && !h->no_side_pads && (n + 31) / 32 <= 64 * (int64_t)F.a.nB) {
                 RowArgs Ap = A;
                 Ap.D = 32;
                 const int64_t keep_kr = h->force_kr;
