@@ -498,7 +498,8 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 const bool tt = F.has_pair && F.tt;
                 const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * (r128(sizeof(FlatTile)) + r128((size_t)M.KR * 4));
                 (void)tt;
-                auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 5 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
+                // (the pair instantiation needs its 63 registers: 4 blocks per SM unless asked otherwise)
+                auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 15 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
                                        : (h->rows_minb == 8 ? k_flat_rows<8, false> : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>)));
                 if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 1;

@@ -255,6 +255,15 @@ def test_flat_pipeline_text_edges(oracle):
         orc = oracle.encode_batch(packed, other, threads=8, **kw)
         assert_matches_oracle(be, orc, what="flat edges pairs %r" % (kw,))
     assert "k_flat_rows" in tok.profile_report()
+    # far more rows than text (empty documents): the pad columns are then written by k_flat_rows itself
+    sparse = pack_strings([""] * 70000 + ["xin chào", "a"] * 5 + [""] * 3000)
+    for kw in (dict(max_len=32), dict(max_len=128)):
+        be = tok.encode_batch(sparse, **kw)
+        orc = oracle.encode_batch(sparse, None, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="flat sparse %r" % (kw,))
+        be = tok.encode_batch(sparse, sparse, **kw)
+        orc = oracle.encode_batch(sparse, sparse, threads=8, **kw)
+        assert_matches_oracle(be, orc, what="flat sparse pairs %r" % (kw,))
     # a chunk that starts in the middle of the caller's buffer (absolute offsets, unaligned base)
     tok2 = Tokenize()
     tok2.set_option("chunk_rows", 777)
