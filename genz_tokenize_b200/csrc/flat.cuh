@@ -433,6 +433,7 @@ struct __align__(16) FlatTile {
     uint32_t dflag[32];
     uint32_t demit[32];
     SeqDesc dsd[32];
+    int32_t tlo[32];               // pairs, the usual row: token types are 1 exactly on [tlo, m) -- else -1 (closed form per quad)
 };
 static const uint32_t FF_AGAIN = 8u;   // the row goes to the generic second pass
 
@@ -605,7 +606,12 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
             ts->dnA[lane] = (int32_t)nws[0];
             ts->dL[lane] = dL;
             ts->dflag[lane] = 0u;
-            if (pair) ts->dsd[lane] = seq_describe((int32_t)nws[0], dL, W);
+            if (pair) {
+                const SeqDesc sd = seq_describe((int32_t)nws[0], dL, W);
+                ts->dsd[lane] = sd;
+                // no residual None, the two None of the framing become 0 / 1 right behind A, no trailing eos id: 0..0 1..1 0..0
+                ts->tlo[lane] = (!sd.err && sd.r1 < 0 && sd.r2 < 0 && sd.f1 == sd.p1 && sd.f2 == sd.p1 + 1 && sd.m < W && sd.p1 > 0) ? sd.p1 + 1 : -1;
+            }
         }
         __syncwarp();
         // ---- 2. the real columns of every row, four lanes per row, four positions per lane and step: ids, mask, token types
@@ -652,7 +658,9 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                 st_cs32(A.mask + grow + j0, mask_word(Lr - j0));
                 if (PAIR && want_tt) {
                     uint32_t ttw, sqw;
-                    seq_words4(ts->dsd[d], j0, W, A.eos_i8, &ttw, &sqw);
+                    const int32_t lo1 = ts->tlo[d];
+                    if (lo1 >= 0) ttw = mask_word(ts->dsd[d].m - j0) & ~mask_word(lo1 - j0);
+                    else seq_words4(ts->dsd[d], j0, W, A.eos_i8, &ttw, &sqw);
                     st_cs32(A.tt + grow + j0, ttw);
                 }
             }
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                 flags = __reduce_or_sync(FULL_MASK, flags);
                 SeqDesc sd;
                 if (pair) sd = seq_describe(nA, dL, W);
-                if (lane == 0) { ts->dnA[dd] = nA; ts->dL[dd] = dL; ts->dflag[dd] |= flags; if (pair) ts->dsd[dd] = sd; }
+                if (lane == 0) { ts->dnA[dd] = nA; ts->dL[dd] = dL; ts->dflag[dd] |= flags; if (pair) { ts->dsd[dd] = sd; ts->tlo[dd] = -1; } }
                 __syncwarp();
                 const int32_t Lr2 = min(dL, W);
                 const size_t g2 = (size_t)(r0 + dd) * (size_t)W;
