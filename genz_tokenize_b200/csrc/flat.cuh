@@ -627,8 +627,17 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
             bool odd = false, special = false;
             const uint32_t a1 = nwA + 1u;                                  // position of the </s> behind A
             const bool cut = L >= W;                                       // truncated: the last column is </s> (tokenize.py:145)
+            // the longest row of the group: behind it every quad of every row is padding (a warp-uniform test, no divergence)
+            const int32_t gmax = __reduce_max_sync(FULL_MASK, live ? Lr : 0);
+            const bool tt_plain = !(PAIR && want_tt) || __all_sync(FULL_MASK, !live || ts->tlo[d] >= 0);
             for (int32_t q = lane & 3; q < qpr && live; q += 4) {
                 const int32_t j0 = q * 4;
+                if ((q & ~3) * 4 >= gmax && tt_plain) {
+                    st_cs128(A.ids + grow + j0, make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad));
+                    st_cs32(A.mask + grow + j0, 0u);
+                    if (PAIR && want_tt) st_cs32(A.tt + grow + j0, 0u);
+                    continue;
+                }
                 // the four words (if any) first: independent loads, one round trip
                 uint32_t val[4]; bool inA[4], inB[4];
 #pragma unroll
