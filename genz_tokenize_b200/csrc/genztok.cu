@@ -9,7 +9,7 @@
 // and for ragged results (no padding / no truncation / max_len None or <= 0)
 //   k_rows<COUNT> -> k_bpe_pending -> k_rows<COUNT> (row list) -> k_row_lens -> k_scan_i64
 //   -> k_rows<RAGGED> -> k_post_rows.
-// Decode is k_decode<false> (lengths) -> k_scan_i64 -> k_decode<true>.
+// Decode is k_decode_len (lengths, trailing pad runs) -> k_scan_i64 -> k_decode_write.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -71,6 +71,8 @@ struct DeviceCtx {
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
     DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
+    DevBuf dec_lead;                              // decode: per-row description left by the length pass for the write pass
+    struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; } dec_sig;   // the batch it describes
     struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok, fixa, fixp; } flat[2];   // byte-parallel pipeline, per side
     // profiling
     bool profiling = false;
@@ -99,6 +101,7 @@ struct genztok {
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
     int64_t rows_minb = 5, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
     int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
+    int64_t no_fixed_decode = 0;         // decode fixed-width rows with the any-rows kernels (test knob)
     int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
     std::map<std::string, std::pair<int64_t, double>> prof_acc;
@@ -611,7 +614,7 @@ void genztok_destroy(genztok_t* h) {
         if (d->stream) cudaStreamSynchronize(d->stream);
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
-                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->slots,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->dec_lead, &d->slots,
                           &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -700,6 +703,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->words_minb = value;
     } else if (n == "no_tma") {
         h->no_tma = value;
+    } else if (n == "no_fixed_decode") {
+        h->no_fixed_decode = value;
     } else if (n == "tma_columns") {
         if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "tma_columns must be 0 (auto) or a multiple of 16 up to 256");
         h->force_kr = value;
@@ -1105,12 +1110,27 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
     CU(cudaSetDevice(d->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     LaunchScope::cur_stream = st;
-    DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes};
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 8));
-    if (!d_bytes) {
+    DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes, nullptr};
+    // one wave of resident blocks (4 per SM by the kernels' launch bounds), rows or tiles of 32 rows by grid stride
+    const unsigned grid_len = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 4));
+    const unsigned grid_write = grid_len;
+    // fixed-width rows of whole 16-byte vectors whose byte counts fit 32 bits: a warp per 32 rows instead of a warp per row
+    const bool fixed = !d_ids_off && width >= 4 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ids) & 15) == 0 &&
+                       (int64_t)width * std::max<int64_t>(1, h->H.max_form) < (1ll << 31) && h->no_fixed_decode == 0;
+    CU(d->dec_lead.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(DecLead)));
+    A.lead = d->dec_lead.as<DecLead>();
+    auto same_batch = [&]() { return d->dec_sig.ids == (const void*)d_ids && d->dec_sig.ids_off == (const void*)d_ids_off && d->dec_sig.out_off == (const void*)d_out_off &&
+                                     d->dec_sig.n == n && d->dec_sig.width == width; };
+    auto length_pass = [&]() -> int {
         CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
         A.out_len = d->out_len.as<int64_t>();
-        if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode<false><<<grid, 256, 0, st>>>(d->T, A); }
+        if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_len_fixed"); k_decode_len_fixed<<<grid_len, 256, 0, st>>>(d->T, A); }
+        else if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode_len<<<grid_len, 256, 0, st>>>(d->T, A); }
+        d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width;
+        return GENZTOK_OK;
+    };
+    if (!d_bytes) {
+        { int rc = length_pass(); if (rc) return rc; }
         { int rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d_out_off, n); if (rc) return rc; }
         if (total_bytes) {
             CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
@@ -1118,7 +1138,10 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
         }
         return GENZTOK_OK;
     }
-    if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode<true><<<grid, 256, 0, st>>>(d->T, A); }
+    // the write pass reads what the length pass of the same batch left in dec_lead; after another batch's length pass it is redone
+    if (!same_batch()) { int rc = length_pass(); if (rc) return rc; }
+    if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_write_fixed"); k_decode_write_fixed<<<grid_write, 256, 0, st>>>(d->T, A); }
+    else if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode_write<<<grid_write, 256, 0, st>>>(d->T, A); }
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }

@@ -84,6 +84,7 @@ struct HostTables {
     std::vector<uint8_t> form_blob;
     std::vector<uint32_t> mid_off, mid_len, last_off, last_len;
     std::vector<uint32_t> mid_desc, last_desc;    // (offset/8) << 8 | min(len,255): one load per id on the device
+    uint32_t max_form = 0;                        // longest decode form in bytes
     int64_t n_ids = 0;
 
     std::string err;
@@ -335,6 +336,8 @@ struct HostTables {
         }
         // one 32-bit descriptor per form: (offset / 8) << 8 | min(len, 255)
         mid_desc.resize((size_t)n_ids + 1); last_desc.resize((size_t)n_ids + 1);
+        max_form = 0;
+        for (size_t i = 0; i < mid_len.size(); i++) max_form = std::max(max_form, std::max(mid_len[i], last_len[i]));
         for (int64_t id = 0; id <= n_ids; id++) {
             mid_desc[(size_t)id] = ((mid_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(mid_len[(size_t)id], 255u);
             last_desc[(size_t)id] = ((last_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(last_len[(size_t)id], 255u);

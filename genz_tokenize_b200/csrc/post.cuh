@@ -209,6 +209,16 @@ __global__ void __launch_bounds__(256) k_post_rows(DevTables T, PostArgs A, cons
 }
 
 // ---- decode (tokenize.py:137-139) ------------------------------------------------------------------
+// What pass 1 leaves per row for pass 2.  A fixed-width row is mostly a run of pad ids behind the real ones: that run decodes to
+// one short form repeated, so pass 2 writes it straight to global memory as 16-byte units of the periodic text and never reads
+// those ids again.  n_lead < 0: no such run (the whole row goes through the staging buffer).
+struct __align__(16) DecLead {
+    int32_t n_lead;       // ids [0, n_lead) are staged; ids [n_lead, n-1) are all pad; id n-1 is the row's last piece
+    int32_t lead_bytes;   // text bytes of ids [0, n_lead)
+    uint32_t last_off;    // the last piece (its "nothing follows" form): offset into the form blob ...
+    uint32_t last_len;    // ... and length
+};
+
 struct DecArgs {
     const int32_t* ids;
     const int64_t* ids_off;   // NULL -> n rows of `width`
@@ -217,6 +227,7 @@ struct DecArgs {
     int64_t* out_len;         // per row bytes (pass 1)
     const int64_t* out_off;   // per row start (pass 2)
     uint8_t* out;
+    DecLead* lead;            // written by pass 1, read by pass 2
 };
 
 __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool last, uint32_t* off, uint32_t* len) {
@@ -229,157 +240,389 @@ __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool la
 
 static const int DEC_CAP = 2048;       // bytes staged per warp before a flush
 static const int DEC_MAXFORM = 32;     // forms longer than this go straight to global memory
+static const int DEC_MINRUN = 8;       // shortest trailing run of pad ids worth the direct path
+static const int DEC_MAXRUNROW = 1 << 26;          // rows longer than this take the staged path only (32-bit byte counts, exact x % L)
+static const int64_t DEC_MAXROW = 0x7FFFFF00ll;    // ids per row (32-bit positions inside a row)
 
-// Pass 1 (WRITE == false): bytes per row.  Pass 2: gather the forms into a per-warp shared-memory staging buffer
-// and write the text with aligned 16-byte stores (edges bytewise: neighbouring rows belong to other warps).
-template <bool WRITE>
-__global__ void __launch_bounds__(256, WRITE ? 4 : 6) k_decode(DevTables T, DecArgs A) {
-    __shared__ __align__(16) uint8_t stage[WRITE ? 8 : 1][WRITE ? DEC_CAP + 16 : 16];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+// the form a pad id decodes to when another piece follows, if it can be written as a periodic text (1..8 bytes)
+__device__ __forceinline__ uint32_t dec_pad_period(const DevTables& T, uint64_t* text) {
+    uint32_t off, len;
+    dec_form(T, T.pad, false, &off, &len);
+    if (len < 1 || len > 8) return 0;
+    *text = *reinterpret_cast<const uint64_t*>(T.form_blob + off);
+    return len;
+}
+// x % L for L in 1..8 and x < 2^29 with M = ceil(2^32 / L): one multiply-high instead of a division
+__device__ __forceinline__ uint32_t dec_mod(uint32_t x, uint32_t L, uint32_t M) { return L == 1u ? 0u : x - __umulhi(x, M) * L; }
+
+// bytes of id's "another piece follows" form; counts the id as real when it is not pad and not the row's last id
+#define DEC_MID(ID, I)                                                        \
+    do {                                                                      \
+        const int32_t _id = (ID);                                             \
+        const uint32_t _k = min((uint32_t)_id, nid);                          \
+        uint32_t _l = T.mid_desc[_k] & 255u;                                  \
+        if (_l == 255u) _l = T.mid_len[_k];                                   \
+        sum += _l;                                                            \
+        if (_id != pad && (I) < lim) hi = (I);                                \
+    } while (0)
+
+// Pass 1: bytes per row, and the description of the row's trailing run of pad ids.  A lane reads four consecutive ids with one
+// 16-byte load where the row is aligned; every id is taken as "followed by another piece" and the row's last id is corrected
+// afterwards by all lanes alike.  One row per warp at a time does not keep enough bytes in flight for HBM (measured: 1.8 TB/s),
+// so the first 256 ids of the warp's next row are loaded before this row is worked on, and the row after that is located.
+__global__ void __launch_bounds__(256, 4) k_decode_len(DevTables T, DecArgs A) {
+    const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint8_t* ob = stage[WRITE ? wib : 0];
-    // The padding of fixed-width rows decodes to one short form repeated: sixteen-byte units of that periodic text, one per
-    // phase, are kept per warp so that a run of pad ids is written as whole units instead of byte by byte.
-    __shared__ __align__(16) uint8_t padtab[WRITE ? 8 : 1][WRITE ? 8 : 1][16];
-    uint32_t padL = 0; uint64_t padP = 0;
-    if (WRITE) {
-        uint32_t off, len;
-        dec_form(T, T.pad, false, &off, &len);
-        if (len >= 1 && len <= 8) {
-            padL = len;
-            padP = *reinterpret_cast<const uint64_t*>(T.form_blob + off);
-            if (lane < (int)len) {
-                int ph = lane;
-                for (int k = 0; k < 16; k++) { padtab[wib][lane][k] = (uint8_t)(padP >> (8 * ph)); ph = ph + 1 == (int)len ? 0 : ph + 1; }
+    const int32_t pad = T.pad;
+    const uint32_t nid = (uint32_t)T.n_ids;                          // index of decoder.get's default (unk_token)
+    uint64_t padP = 0;
+    const uint32_t padL = dec_pad_period(T, &padP);
+    auto locate = [&](uint64_t rr, const int32_t*& p, int& n) {      // row rr: its ids and how many
+        p = A.ids; n = 0;
+        if (rr < (uint64_t)A.n_rows) {
+            const int64_t start = A.ids_off ? A.ids_off[rr] : (int64_t)rr * A.width;
+            const int64_t n64 = A.ids_off ? A.ids_off[rr + 1] - start : A.width;
+            n = (int)(n64 < DEC_MAXROW ? n64 : DEC_MAXROW);
+            p = A.ids + start;
+        }
+    };
+    auto first_ids = [&](const int32_t* p, int n, int4& a, int4& b) {   // ids [4 lane, +4) and [128 + 4 lane, +4) where they are whole vectors
+        a = make_int4(0, 0, 0, 0); b = a;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            if (4 * lane + 3 < n) a = __ldcs(reinterpret_cast<const int4*>(p + 4 * lane));
+            if (128 + 4 * lane + 3 < n) b = __ldcs(reinterpret_cast<const int4*>(p + 128 + 4 * lane));
+        }
+    };
+    const int32_t *ids, *ids1, *ids2;
+    int n, n1, n2;
+    int4 va, vb, va1, vb1;
+    locate(warp, ids, n);
+    locate(warp + nwarps, ids1, n1);
+    first_ids(ids, n, va, vb);
+    for (uint64_t r = warp; r < (uint64_t)A.n_rows; r += nwarps) {
+        locate(r + 2 * nwarps, ids2, n2);
+        first_ids(ids1, n1, va1, vb1);
+        const bool vec = (reinterpret_cast<uintptr_t>(ids) & 15) == 0;
+        const int lim = n - 1;
+        int64_t run = 0;
+        int hi = -1;                                                 // highest index below n-1 whose id is not pad
+        for (int base = 0; base < n; base += 128) {
+            const int i0 = base + 4 * lane;
+            uint32_t sum = 0;
+            if (vec && i0 + 3 < n) {
+                int4 v = va;
+                if (base == 128) v = vb;
+                if (base > 128) v = __ldcs(reinterpret_cast<const int4*>(ids + i0));
+                DEC_MID(v.x, i0); DEC_MID(v.y, i0 + 1); DEC_MID(v.z, i0 + 2); DEC_MID(v.w, i0 + 3);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (i0 + k < n) DEC_MID(ids[i0 + k], i0 + k);
+            }
+            run += __reduce_add_sync(FULL_MASK, sum);
+        }
+        uint32_t last_off = 0, last_len = 0;
+        if (n > 0) {                                                 // the last id: "nothing follows" form instead
+            const int32_t idl = ids[lim];
+            const uint32_t k = min((uint32_t)idl, nid);
+            uint32_t lm = T.mid_desc[k] & 255u;
+            if (lm == 255u) lm = T.mid_len[k];
+            dec_form(T, idl, true, &last_off, &last_len);
+            run += (int64_t)last_len - (int64_t)lm;
+        }
+        if (A.lead) {
+            hi = __reduce_max_sync(FULL_MASK, hi);
+            if (lane == 0) {
+                uint4 d = make_uint4(0xFFFFFFFFu, 0u, last_off, last_len);   // DecLead{n_lead = -1, lead_bytes, last_off, last_len}
+                if (padL && n >= 2 && n < DEC_MAXRUNROW) {
+                    const int cnt = n - 2 - hi;                      // pad ids in [hi + 1, n - 1)
+                    const int64_t lead_bytes = run - last_len - (int64_t)cnt * padL;
+                    if (cnt >= DEC_MINRUN && lead_bytes >= 0 && lead_bytes < (1ll << 31)) { d.x = (uint32_t)(hi + 1); d.y = (uint32_t)lead_bytes; }
+                }
+                *reinterpret_cast<uint4*>(A.lead + r) = d;
             }
         }
+        if (lane == 0) A.out_len[r] = run;
+        ids = ids1; n = n1; va = va1; vb = vb1;
+        ids1 = ids2; n1 = n2;
+    }
+}
+
+// Pass 1 for fixed-width rows (no offsets, width a multiple of four, ids 16-byte aligned, width x longest form < 2^31): a warp
+// takes 32 consecutive rows, reads them as a sequence of 128-id segments with four 16-byte loads in flight per lane, and keeps
+// row j's sums in lane j -- so that the per-row arithmetic (last piece, description of the pad run) and the stores are done
+// once per 32 rows, one row per lane.  The length pass is bound by instruction issue, not memory: 241 -> ~75 per 128 ids.
+__global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArgs A) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int32_t pad = T.pad;
+    const uint32_t nid = (uint32_t)T.n_ids;
+    uint64_t padP = 0;
+    const uint32_t padL = dec_pad_period(T, &padP);
+    const int W = A.width, lim = W - 1;
+    const int nseg = (W + 127) >> 7;
+    const int own_lane = (lim & 127) >> 2;                           // the lane whose last vector ends with the row's last id
+    const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
+    for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
+        const int64_t r0 = (int64_t)tile * 32;
+        const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
+        const int32_t* p = A.ids + r0 * W;
+        const int total = rows * nseg;
+        uint32_t my_run = 0; int my_hi = -1; int32_t my_idl = 0;     // lane j: row r0 + j
+        int row = 0, seg = 0;                                        // the next segment to work on
+        const int32_t* q = p + 4 * lane;                             // this lane's ids of that row
+        uint32_t sum = 0; int hi = -1; int32_t lastv = 0;
+        for (int f0 = 0; f0 < total; f0 += 4) {
+            int4 v[4];
+            {
+                const int32_t* lq = q; int ls = seg;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i0 = 128 * ls + 4 * lane;
+                    v[u] = make_int4(0, 0, 0, 0);
+                    if (f0 + u < total && i0 < W) v[u] = __ldcs(reinterpret_cast<const int4*>(lq + 128 * ls));
+                    if (++ls == nseg) { ls = 0; lq += W; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (f0 + u < total) {
+                    const int i0 = 128 * seg + 4 * lane;
+                    if (i0 < W) {
+                        DEC_MID(v[u].x, i0); DEC_MID(v[u].y, i0 + 1); DEC_MID(v[u].z, i0 + 2); DEC_MID(v[u].w, i0 + 3);
+                        lastv = v[u].w;
+                    }
+                    if (++seg == nseg) {                             // the row is complete
+                        const uint32_t run = __reduce_add_sync(FULL_MASK, sum);
+                        const int rhi = __reduce_max_sync(FULL_MASK, hi);
+                        const int32_t idl = __shfl_sync(FULL_MASK, lastv, own_lane);
+                        if (lane == row) { my_run = run; my_hi = rhi; my_idl = idl; }
+                        sum = 0; hi = -1; seg = 0; row++; q += W;
+                    }
+                }
+            }
+        }
+        if (lane < rows) {                                           // one row per lane: the last id takes its "nothing follows" form
+            const uint32_t k = min((uint32_t)my_idl, nid);
+            uint32_t lm = T.mid_desc[k] & 255u;
+            if (lm == 255u) lm = T.mid_len[k];
+            uint32_t last_off, last_len;
+            dec_form(T, my_idl, true, &last_off, &last_len);
+            const uint32_t run = my_run - lm + last_len;
+            uint4 d = make_uint4(0xFFFFFFFFu, 0u, last_off, last_len);
+            if (padL && W >= 2 && W < DEC_MAXRUNROW) {
+                const int cnt = W - 2 - my_hi;
+                const int64_t lead_bytes = (int64_t)run - last_len - (int64_t)cnt * padL;
+                if (cnt >= DEC_MINRUN && lead_bytes >= 0) { d.x = (uint32_t)(my_hi + 1); d.y = (uint32_t)lead_bytes; }
+            }
+            if (A.lead) *reinterpret_cast<uint4*>(A.lead + r0 + lane) = d;
+            A.out_len[r0 + lane] = run;
+        }
+    }
+}
+#undef DEC_MID
+
+// ---- pass 2 ----
+struct DecWarp {              // what a warp of the write pass keeps across rows
+    uint8_t* ob;              // its staging buffer (DEC_CAP + 16 bytes of shared memory)
+    const uint8_t* padtab;    // [8][16]: sixteen-byte units of the periodic pad text, one per phase
+    uint64_t padP;            // the pad text itself (one period, little endian)
+    uint32_t padL, padM, step;   // period, ceil(2^32 / period), 512 % period
+    int lane;
+};
+
+// One row of the write pass.  `ld` is the row's DecLead (x < 0: no pad run); with a run, its text and the last piece behind it go
+// straight to global memory as 16-byte units of the periodic pad text.  The ids before it are gathered into the warp's staging
+// buffer, one batch of 32 ids at a time with the next batch's ids in flight (`id_first`: this lane's id of the first batch,
+// loaded by the caller ahead of time), and written with aligned 16-byte stores (edges bytewise: neighbouring rows belong to
+// other warps).
+__device__ __forceinline__ void dec_write_row(const DevTables& T, uint8_t* out, const int32_t* ids, int n, int64_t g0, uint4 ld, int32_t id_first,
+                                              const DecWarp& w) {
+    const int lane = w.lane;
+    uint8_t* ob = w.ob;
+    int ne = n;                                             // ids that go through the staging buffer
+    if ((int32_t)ld.x >= 0) {
+        ne = (int32_t)ld.x;
+        const uint32_t L = w.padL, total = (uint32_t)(n - 1 - ne) * L;
+        uint8_t* pp = out + g0 + (int32_t)ld.y;                                     // the run's text starts here
+        const uint32_t h = (0u - (uint32_t)reinterpret_cast<uintptr_t>(pp)) & 15u;  // bytes up to the next unit
+        if (total >= h + 16u) {
+            const uint32_t nu = (total - h) >> 4, tb = h + (nu << 4), t = total - tb;
+            if ((uint32_t)lane < h) pp[lane] = w.padtab[lane];
+            uint32_t ph = dec_mod(h + 16u * lane, L, w.padM);
+            uint4* up = reinterpret_cast<uint4*>(pp + h) + lane;
+            for (uint32_t u = lane; u < nu; u += 32, up += 32) {
+                __stcs(up, *reinterpret_cast<const uint4*>(w.padtab + 16 * ph));
+                ph += w.step; if (ph >= L) ph -= L;
+            }
+            if ((uint32_t)lane < t) pp[tb + lane] = w.padtab[16 * dec_mod(tb, L, w.padM) + lane];
+        } else {
+            for (uint32_t k = lane; k < total; k += 32) pp[k] = (uint8_t)(w.padP >> (8 * dec_mod(k, L, w.padM)));
+        }
+        const uint8_t* src = T.form_blob + ld.z;                                    // the last piece behind the run
+        for (uint32_t k = lane; k < ld.w; k += 32) pp[total + k] = src[k];
+    }
+    uint8_t* gbase = out + (g0 & ~(int64_t)15);             // global address of ob[0]
+    int lead = (int)(g0 & 15);                              // ob[0..lead) is not ours (previous row)
+    int cur = lead;
+    // flush ob[0..upto) (upto multiple of 16, or everything when last): aligned 16-byte stores, foreign/partial units bytewise
+    auto flush = [&](int upto, bool last) {
         __syncwarp();
+        const int nfull = last ? (cur & ~15) : upto;
+        if (lead && nfull && lane >= lead && lane < 16) gbase[lane] = ob[lane];
+        for (int u = (lane + (lead ? 1 : 0)) * 16; u < nfull; u += 512) *reinterpret_cast<uint4*>(gbase + u) = *reinterpret_cast<const uint4*>(ob + u);
+        if (last) {
+            const int rem = cur - nfull;                    // trailing partial unit
+            if (lane < rem) { const int k = nfull + lane; if (!(nfull == 0 && k < lead)) gbase[k] = ob[k]; }
+            return;
+        }
+        __syncwarp();
+        const int rem = cur - nfull;
+        uint8_t keep = 0;
+        if (lane < rem) keep = ob[nfull + lane];
+        __syncwarp();
+        if (lane < rem) ob[lane] = keep;
+        gbase += nfull; cur = rem; lead = 0;
+        __syncwarp();
+    };
+    int32_t idn = id_first;
+    for (int base = 0; base < ne; base += 32) {
+        const int i = base + lane;
+        const int32_t id = idn;
+        if (base + 32 < ne) idn = i + 32 < ne ? ids[i + 32] : 0;           // the next batch's ids in flight
+        uint32_t off = 0, len = 0;
+        if (i < ne) dec_form(T, id, i == n - 1, &off, &len);
+        const uint8_t* src = T.form_blob + off;
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+        const uint32_t maxlen = __reduce_max_sync(FULL_MASK, len);
+        if (maxlen <= (uint32_t)DEC_MAXFORM) {
+            if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
+            uint8_t* d = ob + cur + (incl - len);
+            // Eight bytes per form and round, the rounds and the bytes inside a round from the top down, without a test per byte:
+            // what a form writes behind its own end belongs to a later form of the batch, which writes it in a later
+            // instruction (its byte index there is smaller), or to nobody (behind the batch: 7 bytes of slack, rewritten by
+            // the next batch).
+            for (int k0 = (int)((maxlen - 1u) & ~7u); k0 >= 0 && maxlen; k0 -= 8) {
+                if ((uint32_t)k0 < len) {
+                    const uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);   // forms are 8-byte aligned in the blob
+                    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+                    volatile uint8_t* dk = d + k0;                  // volatile: the stores stay in this order
+                    dk[7] = (uint8_t)(hi >> 24); dk[6] = (uint8_t)(hi >> 16); dk[5] = (uint8_t)(hi >> 8); dk[4] = (uint8_t)hi;
+                    dk[3] = (uint8_t)(lo >> 24); dk[2] = (uint8_t)(lo >> 16); dk[1] = (uint8_t)(lo >> 8); dk[0] = (uint8_t)lo;
+                }
+                __syncwarp();
+            }
+            cur += (int)tot;
+        } else {                                            // rare: a very long vocab entry -> write this batch directly
+            if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */
+                __syncwarp();
+                for (int k = lead + lane; k < cur; k += 32) gbase[k] = ob[k];
+            }
+            uint8_t* d = gbase + cur + (incl - len);
+            for (uint32_t k = 0; k < len; k++) d[k] = src[k];
+            // restart the staging buffer at the new position
+            const int64_t gpos = (gbase - out) + cur + (int64_t)tot;
+            gbase = out + (gpos & ~(int64_t)15);
+            lead = (int)(gpos & 15);
+            cur = lead;
+            __syncwarp();
+        }
+    }
+    flush(0, true);
+    __syncwarp();
+}
+
+__device__ __forceinline__ DecWarp dec_warp_setup(const DevTables& T, uint8_t (*stage)[DEC_CAP + 16], uint8_t (*padtab)[8][16]) {
+    DecWarp w;
+    w.lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    w.ob = stage[wib];
+    w.padP = 0;
+    w.padL = dec_pad_period(T, &w.padP);
+    w.padM = w.padL > 1 ? (uint32_t)((0x100000000ull + w.padL - 1) / w.padL) : 0u;
+    w.step = w.padL ? 512u % w.padL : 0u;
+    if (w.lane < (int)w.padL) {
+        int ph = w.lane;
+        for (int k = 0; k < 16; k++) { padtab[wib][w.lane][k] = (uint8_t)(w.padP >> (8 * ph)); ph = ph + 1 == (int)w.padL ? 0 : ph + 1; }
+    }
+    w.padtab = &padtab[wib][0][0];
+    __syncwarp();
+    return w;
+}
+
+// Pass 2, any rows: a warp per row; the next row's offset and description are fetched while this row is written.
+__global__ void __launch_bounds__(256, 4) k_decode_write(DevTables T, DecArgs A) {
+    __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
+    __shared__ __align__(16) uint8_t padtab[8][8][16];
+    const DecWarp w = dec_warp_setup(T, stage, padtab);
+    const int lane = w.lane;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const bool use_lead = A.lead != nullptr && w.padL != 0;
+    int64_t g0 = 0;
+    uint4 ldw = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+    if (warp < (uint64_t)A.n_rows) {
+        g0 = A.out_off[warp];
+        if (use_lead) ldw = *reinterpret_cast<const uint4*>(A.lead + warp);
     }
     for (uint64_t r = warp; r < (uint64_t)A.n_rows; r += nwarps) {
         const int64_t start = A.ids_off ? A.ids_off[r] : (int64_t)r * A.width;
-        const int64_t n = A.ids_off ? A.ids_off[r + 1] - start : A.width;
+        const int64_t n64 = A.ids_off ? A.ids_off[r + 1] - start : A.width;
+        const int n = (int)(n64 < DEC_MAXROW ? n64 : DEC_MAXROW);
         const int32_t* ids = A.ids + start;
-        if (!WRITE) {
-            int64_t run = 0;
-            for (int64_t base = 0; base < n; base += 256) {              // eight batches of ids in flight
-                int32_t idv[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) { const int64_t i = base + 32 * k + lane; idv[k] = i < n ? ids[i] : 0; }
-                uint32_t sum = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int64_t i = base + 32 * k + lane;
-                    uint32_t off = 0, len = 0;
-                    if (i < n) dec_form(T, idv[k], i == n - 1, &off, &len);
-                    sum += len;
-                }
-                run += __reduce_add_sync(FULL_MASK, sum);
-            }
-            if (lane == 0) A.out_len[r] = run;
-            continue;
-        }
-        const int64_t g0 = A.out_off[r];
-        uint8_t* gbase = A.out + (g0 & ~(int64_t)15);      // global address of ob[0]
-        int lead = (int)(g0 & 15);                          // ob[0..lead) is not ours (previous row)
-        int cur = lead;
-        // flush ob[0..upto) (upto multiple of 16, or everything when last): aligned 16-byte stores, foreign/partial units bytewise
-        auto flush = [&](int upto, bool last) {
-            __syncwarp();
-            const int nfull = last ? (cur & ~15) : upto;
-            for (int u = lane * 16; u < nfull; u += 512) {
-                if (u == 0 && lead) { for (int k = lead; k < 16; k++) gbase[k] = ob[k]; }
-                else *reinterpret_cast<uint4*>(gbase + u) = *reinterpret_cast<const uint4*>(ob + u);
-            }
-            if (last) {
-                const int rem = cur - nfull;                // trailing partial unit
-                if (lane < rem) { const int k = nfull + lane; if (!(nfull == 0 && k < lead)) gbase[k] = ob[k]; }
-                return;
-            }
-            __syncwarp();
-            const int rem = cur - nfull;
-            uint8_t keep = 0;
-            if (lane < rem) keep = ob[nfull + lane];
-            __syncwarp();
-            if (lane < rem) ob[lane] = keep;
-            gbase += nfull; cur = rem; lead = 0;
-            __syncwarp();
-        };
-        for (int64_t base0 = 0; base0 < n; base0 += 256) {
-            int32_t idv[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) { const int64_t i = base0 + 32 * k + lane; idv[k] = i < n ? ids[i] : 0; }
-            uint32_t upad = 0;                                  // batches of this group that are all padding
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int64_t i = base0 + 32 * k + lane;
-                if (__all_sync(FULL_MASK, idv[k] == T.pad && i < n - 1)) upad |= 1u << k;
-            }
-#pragma unroll 1
-            for (int kb = 0; kb < 8; kb++) {
-                const int64_t base = base0 + 32 * kb;
-                if (base >= n) break;
-                // a run of batches that hold nothing but pad ids (and not the row's last id): whole units of the periodic text
-                if (padL && (upad >> kb) & 1u) {
-                    int rl = 1;
-                    while (kb + rl < 8 && ((upad >> (kb + rl)) & 1u)) rl++;
-                    const int L = (int)padL, total = 32 * L * rl;
-                    if (cur + total > DEC_CAP) flush(cur & ~15, false);
-                    const int s0 = cur, s1 = cur + total;
-                    const int a0 = (s0 + 15) & ~15, a1 = s1 & ~15;                       // whole 16-byte units inside [s0, s1)
-                    {
-                        int ph = (a0 - s0 + lane * 16) % L;
-                        const int step = 512 % L;
-                        for (int u = a0 + lane * 16; u < a1; u += 512) {
-                            *reinterpret_cast<uint4*>(ob + u) = *reinterpret_cast<const uint4*>(padtab[wib][ph]);
-                            ph += step; if (ph >= L) ph -= L;
-                        }
-                    }
-                    if (s0 + lane < a0) ob[s0 + lane] = (uint8_t)(padP >> (8 * (lane % L)));
-                    if (a1 + lane < s1) ob[a1 + lane] = (uint8_t)(padP >> (8 * ((a1 - s0 + lane) % L)));
-                    cur += total;
-                    kb += rl - 1;
-                    continue;
-                }
-                const int64_t i = base + lane;
-                int32_t myid = idv[0];
-#pragma unroll
-                for (int k = 1; k < 8; k++) if (kb == k) myid = idv[k];
-                uint32_t off = 0, len = 0;
-                if (i < n) dec_form(T, myid, i == n - 1, &off, &len);
-                const uint8_t* src = T.form_blob + off;
-                uint32_t incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-                const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
-                const bool big = __any_sync(FULL_MASK, len > (uint32_t)DEC_MAXFORM);
-                if (!big) {
-                    if (cur + (int)tot > DEC_CAP) flush(cur & ~15, false);
-                    uint8_t* d = ob + cur + (incl - len);
-                    for (uint32_t k0 = 0; k0 < len; k0 += 8) {              // forms are 8-byte aligned in the blob: one load per 8 bytes
-                        uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);
-                        const uint32_t nb = len - k0 < 8u ? len - k0 : 8u;
-#pragma unroll
-                        for (uint32_t k = 0; k < 8; k++) if (k < nb) d[k0 + k] = (uint8_t)(v >> (8 * k));
-                    }
-                    cur += (int)tot;
-                } else {                                        // rare: a very long vocab entry -> write this batch directly
-                    if (cur > lead || lead) { /* push out what is staged so far, bytewise tail included */
-                        __syncwarp();
-                        for (int k = lead + lane; k < cur; k += 32) gbase[k] = ob[k];
-                    }
-                    uint8_t* d = gbase + cur + (incl - len);
-                    for (uint32_t k = 0; k < len; k++) d[k] = src[k];
-                    // restart the staging buffer at the new position
-                    const int64_t gpos = (gbase - A.out) + cur + (int64_t)tot;
-                    gbase = A.out + (gpos & ~(int64_t)15);
-                    lead = (int)(gpos & 15);
-                    cur = lead;
-                    __syncwarp();
-                }
+        const int64_t g0_cur = g0;
+        const uint4 ld_cur = ldw;
+        const int ne = (int32_t)ld_cur.x >= 0 ? (int32_t)ld_cur.x : n;
+        const int32_t id_first = lane < ne ? ids[lane] : 0;
+        {   // the next row of this warp
+            const uint64_t rn = r + nwarps;
+            if (rn < (uint64_t)A.n_rows) {
+                g0 = A.out_off[rn];
+                if (use_lead) ldw = *reinterpret_cast<const uint4*>(A.lead + rn);
             }
         }
-        flush(0, true);
-        __syncwarp();
+        dec_write_row(T, A.out, ids, n, g0_cur, ld_cur, id_first, w);
+    }
+}
+
+// Pass 2 for fixed-width rows: a warp takes 32 consecutive rows, lane j reads row j's offset and description (coalesced, once
+// per 32 rows) and hands them out by shuffle; the first ids of the next row are loaded before this row is written.
+__global__ void __launch_bounds__(256, 4) k_decode_write_fixed(DevTables T, DecArgs A) {
+    __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
+    __shared__ __align__(16) uint8_t padtab[8][8][16];
+    const DecWarp w = dec_warp_setup(T, stage, padtab);
+    const int lane = w.lane;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const bool use_lead = A.lead != nullptr && w.padL != 0;
+    const int W = A.width;
+    const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
+    for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
+        const int64_t r0 = (int64_t)tile * 32;
+        const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
+        long long my_g0 = 0;
+        uint4 my_ld = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+        if (lane < rows) {
+            my_g0 = A.out_off[r0 + lane];
+            if (use_lead) my_ld = *reinterpret_cast<const uint4*>(A.lead + r0 + lane);
+        }
+        const int32_t* ids = A.ids + r0 * W;
+        int ne_next;
+        { const int x = __shfl_sync(FULL_MASK, (int)my_ld.x, 0); ne_next = x >= 0 ? x : W; }
+        int32_t id_next = lane < ne_next ? ids[lane] : 0;
+        for (int j = 0; j < rows; j++, ids += W) {
+            const int64_t g0 = __shfl_sync(FULL_MASK, my_g0, j);
+            uint4 ld;
+            ld.x = __shfl_sync(FULL_MASK, my_ld.x, j); ld.y = __shfl_sync(FULL_MASK, my_ld.y, j);
+            ld.z = __shfl_sync(FULL_MASK, my_ld.z, j); ld.w = __shfl_sync(FULL_MASK, my_ld.w, j);
+            const int32_t id_first = id_next;
+            if (j + 1 < rows) {
+                const int x = __shfl_sync(FULL_MASK, (int)my_ld.x, j + 1);
+                ne_next = x >= 0 ? x : W;
+                id_next = lane < ne_next ? ids[W + lane] : 0;
+            }
+            dec_write_row(T, A.out, ids, W, g0, ld, id_first, w);
+        }
     }
 }
 

@@ -288,6 +288,104 @@ def test_decode_roundtrip_batch(tok, oracle):
     assert tok.decode_batch(big["input_ids"]) == oracle.decode_batch(big["input_ids"].reshape(-1), np.arange(0, 30000 * 16 + 1, 16, dtype=np.int64), threads=8)
 
 
+def _pad_run_rows(rng, n_rows, width, pad, vocab, exotic):
+    """Fixed-width id rows shaped like encoder output and unlike it: real ids, pad runs at the end / in the middle / at the
+    start, a non-pad last id behind a run, whole rows of pads, out-of-range ids."""
+    ids = np.full((n_rows, width), pad, dtype=np.int32)
+    for r in range(n_rows):
+        kind = rng.integers(0, 8)
+        nl = int(rng.integers(0, width + 1))
+        if kind == 0:
+            nl = 0
+        elif kind == 1:
+            nl = width
+        ids[r, :nl] = rng.integers(0, vocab, nl)
+        if kind == 2 and nl:                                  # pads inside the real part
+            k = rng.integers(0, nl, max(1, nl // 3))
+            ids[r, k] = pad
+        if kind == 3 and width:                               # something behind the run
+            ids[r, width - 1] = rng.integers(0, vocab)
+        if kind == 4 and width >= 3 and nl < width:                          # a second island in the run
+            ids[r, int(rng.integers(nl, width))] = rng.integers(0, vocab)
+        if kind == 5 and nl:
+            ids[r, rng.integers(0, nl)] = exotic[rng.integers(0, len(exotic))]
+    return ids
+
+
+def test_decode_pad_runs(tok, oracle):
+    # the write pass sends the trailing run of pad ids and the last piece straight to global memory: every width around the
+    # 16-byte units and the 32-id batches, every shape of row, against the oracle
+    rng = np.random.default_rng(77)
+    exotic = [-1, -2**31, 2**31 - 1, 48423, 48422, 10**6, 3, 4]
+    from genz_tokenize_b200 import Tokenize
+    any_rows = Tokenize()
+    any_rows.set_option("no_fixed_decode", 1)            # widths that are a multiple of 4 through the warp-per-row kernels too
+    for width in [1, 2, 3, 4, 7, 8, 9, 10, 11, 12, 16, 17, 31, 32, 33, 40, 64, 100, 124, 128, 132, 252, 255, 256, 257, 260, 300, 384, 516]:
+        ids = _pad_run_rows(rng, 300, width, 0, 48423, exotic)
+        ref = oracle.decode_batch(ids.reshape(-1), np.arange(0, 300 * width + 1, width, dtype=np.int64), threads=8)
+        assert tok.decode_batch(ids) == ref, width
+        assert any_rows.decode_batch(ids) == ref, width
+    for n_rows in [1, 31, 32, 33, 64, 65]:                # tiles of 32 rows, whole and partial
+        ids = _pad_run_rows(rng, n_rows, 128, 0, 48423, exotic)
+        assert tok.decode_batch(ids) == oracle.decode_batch(ids.reshape(-1), np.arange(0, n_rows * 128 + 1, 128, dtype=np.int64)), n_rows
+    # ragged rows of the same shapes (rows start at any alignment: the scalar id loads of the length pass)
+    rows = [_pad_run_rows(rng, 1, int(w), 0, 48423, exotic)[0] for w in rng.integers(0, 200, 700)]
+    off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    flat = np.concatenate(rows).astype(np.int32)
+    assert tok.decode_batch(flat, off) == oracle.decode_batch(flat, off, threads=8)
+    # one very long row, mostly padding
+    long_row = np.zeros((3, 70001), dtype=np.int32)
+    long_row[:, :900] = rng.integers(0, 48423, (3, 900))
+    long_row[1, -1] = 770
+    assert tok.decode_batch(long_row) == oracle.decode_batch(long_row.reshape(-1), np.arange(0, 3 * 70001 + 1, 70001, dtype=np.int64))
+    long4 = np.ascontiguousarray(long_row[:, :70000])
+    long4[2, 69990:] = 5
+    assert tok.decode_batch(long4) == oracle.decode_batch(long4.reshape(-1), np.arange(0, 3 * 70000 + 1, 70000, dtype=np.int64))
+
+
+def test_decode_pad_runs_custom_pad_tokens():
+    # pad texts of other periods: "[P] " (4 bytes, divides the unit), "\x7f" ("\x7f@@ " with the marker removed: 1 byte), "Ω" (2),
+    # "a~b " (4), "ặ~ " (5), "abcdefg " (8), "abcdefgh " / "<padtok> " (9 bytes: no periodic shortcut), and strings that
+    # vocab.txt holds too ("ab", "p@@": the pad id moves, SURVEY A.6)
+    from genz_tokenize_b200 import Tokenize
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(78)
+    for pad_tok in ["[P]", "\x7f@@", "Ω@@", "zq@@", "a~b", "ặ~", "abcdefg", "abcdefgh", "<padtok>", "ab", "p@@"]:
+        sp = [pad_tok, "<s>", "</s>", "<mask>", "<unk>"]
+        t, o = Tokenize(*sp), Oracle(specials=sp)
+        pad = t.encoder[pad_tok]                      # 0 unless vocab.txt holds the same string (then it moved: SURVEY A.6)
+        for width in [5, 16, 37, 128, 260]:
+            ids = _pad_run_rows(rng, 200, width, pad, t.vocab_size(), [-1, 10**6, 1, 2, 0])
+            assert t.decode_batch(ids) == o.decode_batch(ids.reshape(-1), np.arange(0, 200 * width + 1, width, dtype=np.int64)), (pad_tok, width)
+
+
+def test_decode_device_interleaved_batches(tok):
+    # length pass of A, length pass of B, write pass of A: the per-row description of A was overwritten and is redone
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(79)
+    dev = torch.device("cuda:0")
+    a = _pad_run_rows(rng, 500, 64, 0, 48423, [-1])
+    b = _pad_run_rows(rng, 500, 64, 0, 48423, [-1])
+    da, db = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    oa, ob_ = torch.empty(501, dtype=torch.int64, device=dev), torch.empty(501, dtype=torch.int64, device=dev)
+    ta, tb = C.c_int64(), C.c_int64()
+    st = tok._torch_stream(dev)
+    lib, h = tok._lib, tok._h
+    assert lib.genztok_decode_device(h, 0, da.data_ptr(), None, 500, 64, oa.data_ptr(), None, C.byref(ta), st) == 0
+    assert lib.genztok_decode_device(h, 0, db.data_ptr(), None, 500, 64, ob_.data_ptr(), None, C.byref(tb), st) == 0
+    xa = torch.zeros(ta.value + 16, dtype=torch.uint8, device=dev)
+    xb = torch.zeros(tb.value + 16, dtype=torch.uint8, device=dev)
+    assert lib.genztok_decode_device(h, 0, da.data_ptr(), None, 500, 64, oa.data_ptr(), xa.data_ptr(), None, st) == 0
+    assert lib.genztok_decode_device(h, 0, db.data_ptr(), None, 500, 64, ob_.data_ptr(), xb.data_ptr(), None, st) == 0
+    torch.cuda.synchronize()
+    for ids, x, o, tot in [(a, xa, oa, ta), (b, xb, ob_, tb)]:
+        raw, off = x.cpu().numpy().tobytes(), o.cpu().numpy()
+        assert off[-1] == tot.value
+        assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(500)] == tok.decode_batch(ids)
+        assert raw[tot.value:] == bytes(16)              # nothing written behind the text
+
+
 def test_device_api_matches_host_api(tok):
     import torch
     from genz_tokenize_b200 import workload
