@@ -300,7 +300,15 @@ def main():
         extra["encode_pairs_256"] = {"tokens_per_s": ptok / (ms * 1e-3), "pairs_per_s": n / (ms * 1e-3), "ms": ms, "input_gb_per_s": (in_bytes + pbytes) / (ms * 1e-3) / 1e9,
                                      "alg_gb_per_s": palg / (ms * 1e-3) / 1e9, "hbm_frac": palg / (ms * 1e-3) / 1e9 / peak0,
                                      "planes": "input_ids int32 + attention_mask uint8 + token_type_ids int8 [n,256]"}
-        del pout, d_pair, d_poff, tok2
+        # decode of the [n,256] pair rows (BASELINE configs[3] at one GPU's share of 1,048,576 rows)
+        holder = {}
+        ms = timed(lambda: holder.__setitem__("d", tok2.decode_device(pout["input_ids"])))
+        dbytes = int(holder["d"][0].numel())
+        dalg = 4 * n * W2 + dbytes + 8 * (n + 1)
+        extra["decode_padded_rows_256"] = {"rows_per_s": n / (ms * 1e-3), "ids_per_s": n * W2 / (ms * 1e-3), "ms": ms, "text_bytes": dbytes,
+                                           "alg_gb_per_s": dalg / (ms * 1e-3) / 1e9, "hbm_frac": dalg / (ms * 1e-3) / 1e9 / peak0,
+                                           "note": "includes the allocation of the text tensor and one device->host read of the total size"}
+        del holder, pout, d_pair, d_poff, tok2
 
     clocks = sampler.stop()
     # ---- max over ranks --------------------------------------------------------------------------------

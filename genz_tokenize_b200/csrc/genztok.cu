@@ -1111,12 +1111,12 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     LaunchScope::cur_stream = st;
     DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes, nullptr};
-    // one wave of resident blocks (4 per SM by the kernels' launch bounds), rows or tiles of 32 rows by grid stride
-    const unsigned grid_len = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 4));
-    const unsigned grid_write = grid_len;
     // fixed-width rows of whole 16-byte vectors whose byte counts fit 32 bits: a warp per 32 rows instead of a warp per row
     const bool fixed = !d_ids_off && width >= 4 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ids) & 15) == 0 &&
                        (int64_t)width * std::max<int64_t>(1, h->H.max_form) < (1ll << 31) && h->no_fixed_decode == 0;
+    // one wave of resident blocks (4 per SM by the kernels' launch bounds, 5 for k_decode_write_fixed), rows or tiles of 32 rows by grid stride
+    const unsigned grid_len = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 4));
+    const unsigned grid_write = fixed ? (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 5)) : grid_len;
     CU(d->dec_lead.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(DecLead)));
     A.lead = d->dec_lead.as<DecLead>();
     auto same_batch = [&]() { return d->dec_sig.ids == (const void*)d_ids && d->dec_sig.ids_off == (const void*)d_ids_off && d->dec_sig.out_off == (const void*)d_out_off &&

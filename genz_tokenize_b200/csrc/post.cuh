@@ -450,6 +450,7 @@ __device__ __forceinline__ void dec_write_row(const DevTables& T, uint8_t* out, 
             if ((uint32_t)lane < h) pp[lane] = w.padtab[lane];
             uint32_t ph = dec_mod(h + 16u * lane, L, w.padM);
             uint4* up = reinterpret_cast<uint4*>(pp + h) + lane;
+#pragma unroll 1
             for (uint32_t u = lane; u < nu; u += 32, up += 32) {
                 __stcs(up, *reinterpret_cast<const uint4*>(w.padtab + 16 * ph));
                 ph += w.step; if (ph >= L) ph -= L;
@@ -459,6 +460,7 @@ __device__ __forceinline__ void dec_write_row(const DevTables& T, uint8_t* out, 
             for (uint32_t k = lane; k < total; k += 32) pp[k] = (uint8_t)(w.padP >> (8 * dec_mod(k, L, w.padM)));
         }
         const uint8_t* src = T.form_blob + ld.z;                                    // the last piece behind the run
+#pragma unroll 1
         for (uint32_t k = lane; k < ld.w; k += 32) pp[total + k] = src[k];
     }
     uint8_t* gbase = out + (g0 & ~(int64_t)15);             // global address of ob[0]
@@ -469,6 +471,7 @@ __device__ __forceinline__ void dec_write_row(const DevTables& T, uint8_t* out, 
         __syncwarp();
         const int nfull = last ? (cur & ~15) : upto;
         if (lead && nfull && lane >= lead && lane < 16) gbase[lane] = ob[lane];
+#pragma unroll 1
         for (int u = (lane + (lead ? 1 : 0)) * 16; u < nfull; u += 512) *reinterpret_cast<uint4*>(gbase + u) = *reinterpret_cast<const uint4*>(ob + u);
         if (last) {
             const int rem = cur - nfull;                    // trailing partial unit
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(256, 4) k_decode_write(DevTables T, DecArgs A)
 
 // Pass 2 for fixed-width rows: a warp takes 32 consecutive rows, lane j reads row j's offset and description (coalesced, once
 // per 32 rows) and hands them out by shuffle; the first ids of the next row are loaded before this row is written.
-__global__ void __launch_bounds__(256, 4) k_decode_write_fixed(DevTables T, DecArgs A) {
+__global__ void __launch_bounds__(256, 5) k_decode_write_fixed(DevTables T, DecArgs A) {
     __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
     __shared__ __align__(16) uint8_t padtab[8][8][16];
     const DecWarp w = dec_warp_setup(T, stage, padtab);
