@@ -1100,13 +1100,13 @@ namespace {
 extern "C" {
 
 // ---- decode -------------------------------------------------------------------------------------------
-int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
-                          uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
-    if (!h) return GENZTOK_E_INVALID;
-    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
-    if (n < 0 || !d_out_off || (!d_ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: bad arguments");
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceCtx* d = h->devs[(size_t)dev];
+}  // extern "C"
+
+namespace {
+
+// Both passes of the decode on one device; the caller holds h->mu (or owns the device context, as the workers of genztok_decode do).
+int decode_on_device(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                     uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
     CU(cudaSetDevice(d->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     LaunchScope::cur_stream = st;
@@ -1146,6 +1146,19 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
     return GENZTOK_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                          uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_out_off || (!d_ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return decode_on_device(h, h->devs[(size_t)dev], d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, stream);
+}
+
 void genztok_free_text(genztok_t* h, genztok_text_t* out) {
     if (!out || !out->_owner) return;
     OutBlock* ob = reinterpret_cast<OutBlock*>(out->_owner);
@@ -1158,60 +1171,101 @@ void genztok_free_text(genztok_t* h, genztok_text_t* out) {
     memset(out, 0, sizeof *out);
 }
 
+}  // extern "C"
+
+namespace {
+
+struct DecodePart { int rc = GENZTOK_OK; std::vector<uint8_t> bytes; std::vector<int64_t> off; };   // off: row ends relative to the part's start
+
+// Rows [r0, r1) on one device, in chunks of chunk_rows: ids up, both passes, text and offsets down.
+void decode_rows_on_device(genztok_t* h, DeviceCtx* d, const int32_t* ids, const int64_t* ids_off, int32_t width, int64_t r0, int64_t r1, DecodePart* P) {
+    cudaSetDevice(d->device);
+    cudaStream_t st = d->stream;
+    const int64_t rows_per_chunk = std::max<int64_t>(1, h->chunk_rows);
+    P->off.reserve((size_t)(r1 - r0));
+    int64_t total_all = 0;
+    std::vector<int64_t> offs;
+    for (int64_t c0 = r0; c0 < r1 && P->rc == GENZTOK_OK; c0 += rows_per_chunk) {
+        const int64_t c1 = std::min(r1, c0 + rows_per_chunk), m = c1 - c0;
+        const int64_t i0 = ids_off ? ids_off[c0] : c0 * width, i1 = ids_off ? ids_off[c1] : c1 * width, ni = i1 - i0;
+        cudaError_t e;
+        if ((e = d->ids.ensure((size_t)ni * 4 + 16)) != cudaSuccess || (e = d->row_off.ensure((size_t)(m + 1) * 8)) != cudaSuccess ||
+            (e = d->toff.ensure((size_t)(m + 1) * 8)) != cudaSuccess) { P->rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        if (ni) cudaMemcpyAsync(d->ids.p, ids + i0, (size_t)ni * 4, cudaMemcpyHostToDevice, st);
+        const int64_t* d_ioff = nullptr;
+        if (ids_off) { cudaMemcpyAsync(d->toff.p, ids_off + c0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st); d_ioff = d->toff.as<int64_t>(); }
+        int64_t total = 0;
+        P->rc = decode_on_device(h, d, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), nullptr, &total, st);
+        if (P->rc) break;
+        if ((e = d->text.ensure((size_t)total + 16)) != cudaSuccess) { P->rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        P->rc = decode_on_device(h, d, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), d->text.as<uint8_t>(), nullptr, st);
+        if (P->rc) break;
+        offs.resize((size_t)m + 1);
+        const size_t old = P->bytes.size();
+        P->bytes.resize(old + (size_t)total);
+        if (total) cudaMemcpyAsync(P->bytes.data() + old, d->text.p, (size_t)total, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { P->rc = fail(h, GENZTOK_E_CUDA, "decode: %s", cudaGetErrorString(e)); break; }
+        for (int64_t i = 1; i <= m; i++) P->off.push_back(total_all + offs[(size_t)i]);
+        total_all += total;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
 int genztok_decode(genztok_t* h, const int32_t* ids, const int64_t* ids_off, int64_t n, int32_t width, genztok_text_t* out) {
     if (!h) return GENZTOK_E_INVALID;
     if (!out || n < 0 || (!ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode: bad arguments");
     if (h->devs.empty()) return fail(h, GENZTOK_E_NODEVICE, "this handle was created without a CUDA device; there is no CPU path");
     memset(out, 0, sizeof *out);
-    DeviceCtx* d = h->devs[0];
+    std::lock_guard<std::mutex> lk(h->mu);
     OutBlock* ob = new OutBlock();
-    int64_t* off = nullptr; uint8_t* bytes = nullptr;
-    int rc = GENZTOK_OK;
-    {
-        std::lock_guard<std::mutex> lk(h->mu);
-        off = out_alloc<int64_t>(h, ob, (size_t)n + 1);
-    }
+    int64_t* off = out_alloc<int64_t>(h, ob, (size_t)n + 1);
     if (!off) { delete ob; return fail(h, GENZTOK_E_NOMEM, "pinned host allocation failed"); }
     off[0] = 0;
-    const int64_t rows_per_chunk = std::max<int64_t>(1, h->chunk_rows);
-    std::vector<uint8_t> acc;
-    cudaSetDevice(d->device);
-    cudaStream_t st = d->stream;
-    int64_t total_all = 0;
-    for (int64_t r0 = 0; r0 < n && rc == GENZTOK_OK; r0 += rows_per_chunk) {
-        const int64_t r1 = std::min(n, r0 + rows_per_chunk), m = r1 - r0;
-        const int64_t i0 = ids_off ? ids_off[r0] : r0 * width, i1 = ids_off ? ids_off[r1] : r1 * width, ni = i1 - i0;
-        cudaError_t e;
-        if ((e = d->ids.ensure((size_t)ni * 4 + 16)) != cudaSuccess || (e = d->row_off.ensure((size_t)(m + 1) * 8)) != cudaSuccess ||
-            (e = d->toff.ensure((size_t)(m + 1) * 8)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-        if (ni) cudaMemcpyAsync(d->ids.p, ids + i0, (size_t)ni * 4, cudaMemcpyHostToDevice, st);
-        const int64_t* d_ioff = nullptr;
-        if (ids_off) { cudaMemcpyAsync(d->toff.p, ids_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st); d_ioff = d->toff.as<int64_t>(); }
-        int64_t total = 0;
-        rc = genztok_decode_device(h, 0, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), nullptr, &total, st);
-        if (rc) break;
-        if ((e = d->text.ensure((size_t)total + 16)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-        rc = genztok_decode_device(h, 0, d->ids.as<int32_t>() - (ids_off ? i0 : 0), d_ioff, m, width, d->row_off.as<int64_t>(), d->text.as<uint8_t>(), nullptr, st);
-        if (rc) break;
-        std::vector<int64_t> offs((size_t)m + 1);
-        const size_t old = acc.size();
-        acc.resize(old + (size_t)total);
-        if (total) cudaMemcpyAsync(acc.data() + old, d->text.p, (size_t)total, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = fail(h, GENZTOK_E_CUDA, "decode: %s", cudaGetErrorString(e)); break; }
-        for (int64_t i = 1; i <= m; i++) off[r0 + i] = total_all + offs[(size_t)i];
-        total_all += total;
+    // Shard by row across the handle's devices: contiguous row ranges balanced by ids, one host thread per
+    // device, no collective; the parts' texts are concatenated and their offsets shifted.
+    const int G = (int)h->devs.size();
+    std::vector<int64_t> dcut((size_t)G + 1, n);
+    dcut[0] = 0;
+    if (G > 1 && n >= 2 * G) {
+        auto weight = [&](int64_t r) { return (ids_off ? ids_off[r] - ids_off[0] : r * (int64_t)width) + 16 * r; };
+        const int64_t wtot = weight(n);
+        for (int g = 1; g < G; g++) {
+            const int64_t want = wtot * g / G;
+            int64_t lo = dcut[(size_t)g - 1], hi = n;
+            while (lo < hi) { int64_t mid = (lo + hi) / 2; if (weight(mid) < want) lo = mid + 1; else hi = mid; }
+            dcut[(size_t)g] = lo;
+        }
     }
-    if (rc) {
-        std::lock_guard<std::mutex> lk(h->mu);
-        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
-        delete ob;
-        return rc;
+    std::vector<DecodePart> parts((size_t)G);
+    if (G == 1 || n < 2 * G) {
+        decode_rows_on_device(h, h->devs[0], ids, ids_off, width, 0, n, &parts[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() { decode_rows_on_device(h, h->devs[(size_t)g], ids, ids_off, width, dcut[(size_t)g], dcut[(size_t)g + 1], &parts[(size_t)g]); });
+        for (auto& t : th) t.join();
     }
-    bytes = (uint8_t*)malloc(std::max<size_t>(acc.size(), 16));
-    if (!acc.empty()) memcpy(bytes, acc.data(), acc.size());
+    for (auto& pt : parts)
+        if (pt.rc) {
+            for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+            delete ob;
+            return pt.rc;
+        }
+    size_t total_all = 0;
+    for (auto& pt : parts) total_all += pt.bytes.size();
+    uint8_t* bytes = (uint8_t*)malloc(std::max<size_t>(total_all, 16));
     ob->mallocs.push_back(bytes);
-    out->n = n; out->total = total_all; out->bytes = bytes; out->off = off; out->_owner = ob;
+    int64_t base = 0, row = 0;
+    for (auto& pt : parts) {
+        if (!pt.bytes.empty()) memcpy(bytes + base, pt.bytes.data(), pt.bytes.size());
+        for (int64_t v : pt.off) off[++row] = base + v;
+        base += (int64_t)pt.bytes.size();
+    }
+    out->n = n; out->total = (int64_t)total_all; out->bytes = bytes; out->off = off; out->_owner = ob;
     return GENZTOK_OK;
 }
 

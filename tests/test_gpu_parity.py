@@ -517,5 +517,11 @@ def test_one_handle_many_devices(oracle):
     be = multi.encode_batch(t, None, return_offset=True)
     orc = oracle.encode_batch(t, None, return_offset=True, threads=8)
     assert np.array_equal(be["span_off"], orc["span_off"]) and np.array_equal(be["spans"], orc["span"])
+    # decode shards by row the same way: parts concatenated, offsets shifted
+    fix = multi.encode_batch(t, p, max_len=64)["input_ids"]
+    assert multi.decode_batch(fix) == oracle.decode_batch(fix.reshape(-1), np.arange(0, 20000 * 64 + 1, 64, dtype=np.int64), threads=8)
+    rag = multi.encode_batch(t, p)
+    assert multi.decode_batch(rag["input_ids"], rag["row_off"]) == oracle.decode_batch(rag["input_ids"], rag["row_off"], threads=8)
+    assert multi.decode_batch(fix[:3]) == oracle.decode_batch(fix[:3].reshape(-1), np.arange(0, 3 * 64 + 1, 64, dtype=np.int64))
     few = multi.encode_batch((t[0][:t[1][3]], t[1][:4]), max_len=16)       # fewer rows than 2 x devices: one device does it all
     assert np.array_equal(few["input_ids"].reshape(-1), oracle.encode_batch((t[0][:t[1][3]], t[1][:4]), None, max_len=16)["ids"])
