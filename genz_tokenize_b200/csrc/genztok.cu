@@ -72,7 +72,9 @@ struct DeviceCtx {
     DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
     DevBuf slots, key_arena, tok_arena, pending, ctr;
     DevBuf dec_lead;                              // decode: per-row description left by the length pass for the write pass
-    struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; } dec_sig;   // the batch it describes
+    DevBuf tok_flag, tok_len, tok_pos;            // decode of ragged rows by id: last-of-row flags, bytes per id, their scan
+    int64_t tok_base = 0, tok_n = -1;             // the ids that scan describes
+    struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; int by_id = 0; } dec_sig;   // the batch it describes
     struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok, fixa, fixp; } flat[2];   // byte-parallel pipeline, per side
     // profiling
     bool profiling = false;
@@ -101,6 +103,7 @@ struct genztok {
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
     int64_t rows_minb = 5, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
     int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
+    int64_t no_token_decode = 0;         // decode ragged rows with a warp per row instead of a thread per id (test knob)
     int64_t no_fixed_decode = 0;         // decode fixed-width rows with the any-rows kernels (test knob)
     int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
@@ -614,7 +617,7 @@ void genztok_destroy(genztok_t* h) {
         if (d->stream) cudaStreamSynchronize(d->stream);
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
-                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->dec_lead, &d->slots,
+                          &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->dec_lead, &d->tok_flag, &d->tok_len, &d->tok_pos, &d->slots,
                           &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -705,6 +708,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->no_tma = value;
     } else if (n == "no_fixed_decode") {
         h->no_fixed_decode = value;
+    } else if (n == "no_token_decode") {
+        h->no_token_decode = value;
     } else if (n == "tma_columns") {
         if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "tma_columns must be 0 (auto) or a multiple of 16 up to 256");
         h->force_kr = value;
@@ -1119,14 +1124,57 @@ int decode_on_device(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int
     const unsigned grid_write = fixed ? (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 5)) : grid_len;
     CU(d->dec_lead.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(DecLead)));
     A.lead = d->dec_lead.as<DecLead>();
-    auto same_batch = [&]() { return d->dec_sig.ids == (const void*)d_ids && d->dec_sig.ids_off == (const void*)d_ids_off && d->dec_sig.out_off == (const void*)d_out_off &&
-                                     d->dec_sig.n == n && d->dec_sig.width == width; };
+    auto same_batch = [&](int by_id_) { return d->dec_sig.ids == (const void*)d_ids && d->dec_sig.ids_off == (const void*)d_ids_off && d->dec_sig.out_off == (const void*)d_out_off &&
+                                               d->dec_sig.n == n && d->dec_sig.width == width && d->dec_sig.by_id == by_id_; };
+    // Ragged rows: one thread per id (k_dectok_*).  The host needs the number of ids for that: one small read of the offsets.
+    const bool by_id = d_ids_off && n > 0 && h->no_token_decode == 0;
+    auto length_pass_by_id = [&]() -> int {
+        int64_t ends[2] = {0, 0};
+        CU(cudaMemcpyAsync(&ends[0], d_ids_off, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&ends[1], d_ids_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int64_t N = ends[1] - ends[0];
+        if (N < 0) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: id offsets decrease");
+        if (N > (1ll << 28)) return 1;                              // too many ids for the per-id work arrays: warp per row
+        CU(d->tok_flag.ensure((size_t)N + 16)); CU(d->tok_len.ensure((size_t)(N + 1) * 8)); CU(d->tok_pos.ensure((size_t)(N + 2) * 8));
+        DecTokArgs K{d_ids, d_ids_off, n, ends[0], N, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, nullptr};
+        CU(cudaMemsetAsync(K.flag, 0, (size_t)N + 16, st));
+        { LaunchScope ls(h, d, "k_dectok_flags"); k_dectok_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(K); }
+        if (N > 0) { LaunchScope ls(h, d, "k_dectok_len"); k_dectok_len<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d->T, K); }
+        { int rc = launch_scan(h, d, st, K.len, d->tok_pos.as<int64_t>(), N); if (rc) return rc; }
+        { LaunchScope ls(h, d, "k_dectok_rowoff"); k_dectok_rowoff<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(K); }
+        CU(cudaGetLastError());
+        d->tok_base = ends[0]; d->tok_n = N;
+        d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width; d->dec_sig.by_id = 1;
+        return GENZTOK_OK;
+    };
+    if (by_id) {
+        int rc = GENZTOK_OK;
+        if (!d_bytes || !same_batch(1) || d->tok_n < 0) {
+            rc = length_pass_by_id();
+            if (rc < 0) return rc;
+        }
+        if (rc == GENZTOK_OK) {
+            if (!d_bytes) {
+                if (total_bytes) {
+                    CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                }
+                return GENZTOK_OK;
+            }
+            DecTokArgs K{d_ids, d_ids_off, n, d->tok_base, d->tok_n, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, d_bytes};
+            if (K.n_ids > 0) { LaunchScope ls(h, d, "k_dectok_write"); k_dectok_write<<<(unsigned)((K.n_ids + 255) / 256), 256, 0, st>>>(d->T, K); }
+            CU(cudaGetLastError());
+            return GENZTOK_OK;
+        }
+        d->tok_n = -1;                                              // rc == 1: fall through to the warp-per-row kernels
+    } else d->tok_n = -1;
     auto length_pass = [&]() -> int {
         CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
         A.out_len = d->out_len.as<int64_t>();
         if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_len_fixed"); k_decode_len_fixed<<<grid_len, 256, 0, st>>>(d->T, A); }
         else if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode_len<<<grid_len, 256, 0, st>>>(d->T, A); }
-        d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width;
+        d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width; d->dec_sig.by_id = 0;
         return GENZTOK_OK;
     };
     if (!d_bytes) {
@@ -1139,7 +1187,7 @@ int decode_on_device(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int
         return GENZTOK_OK;
     }
     // the write pass reads what the length pass of the same batch left in dec_lead; after another batch's length pass it is redone
-    if (!same_batch()) { int rc = length_pass(); if (rc) return rc; }
+    if (!same_batch(0)) { int rc = length_pass(); if (rc) return rc; }
     if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_write_fixed"); k_decode_write_fixed<<<grid_write, 256, 0, st>>>(d->T, A); }
     else if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode_write<<<grid_write, 256, 0, st>>>(d->T, A); }
     CU(cudaGetLastError());

@@ -629,6 +629,59 @@ __global__ void __launch_bounds__(256, 5) k_decode_write_fixed(DevTables T, DecA
     }
 }
 
+// ---- decode of ragged rows, one thread per id ------------------------------------------------------------
+// Short ragged rows (about twenty ids each once the padding is trimmed) leave a warp per row mostly idle and pay its per-row
+// arithmetic a million times.  Here every id is a thread: lengths per id, one scan over all ids, then each thread copies its
+// form to where the scan says; neighbouring threads write neighbouring text.  Row offsets are the scan read at the row starts.
+struct DecTokArgs {
+    const int32_t* ids;       // ids of the whole batch; this chunk's ids are [base, base + n_ids)
+    const int64_t* ids_off;   // n_rows + 1
+    int64_t n_rows, base, n_ids;
+    uint8_t* flag;            // n_ids: 1 = the id is the last of its row ("nothing follows" form)
+    int64_t* len;             // n_ids: bytes per id
+    const int64_t* pos;       // n_ids + 1: exclusive scan of len
+    int64_t* out_off;         // n_rows + 1
+    uint8_t* out;
+};
+
+__global__ void k_dectok_flags(DecTokArgs A) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_rows) return;
+    const int64_t b = A.ids_off[r] - A.base, e = A.ids_off[r + 1] - A.base;
+    if (e > b && b >= 0 && e <= A.n_ids) A.flag[e - 1] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_dectok_len(DevTables T, DecTokArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_ids) return;
+    uint32_t off, len;
+    dec_form(T, A.ids[A.base + i], A.flag[i] != 0, &off, &len);
+    A.len[i] = len;
+}
+
+__global__ void k_dectok_rowoff(DecTokArgs A) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > A.n_rows) return;
+    int64_t b = A.ids_off[r] - A.base;
+    b = b < 0 ? 0 : (b > A.n_ids ? A.n_ids : b);
+    A.out_off[r] = A.pos[b];
+}
+
+__global__ void __launch_bounds__(256) k_dectok_write(DevTables T, DecTokArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_ids) return;
+    uint32_t off, len;
+    dec_form(T, A.ids[A.base + i], A.flag[i] != 0, &off, &len);
+    const uint8_t* src = T.form_blob + off;
+    uint8_t* d = A.out + A.pos[i];
+    for (uint32_t k0 = 0; k0 < len; k0 += 8) {                   // forms are 8-byte aligned in the blob: one load per 8 bytes
+        const uint64_t v = *reinterpret_cast<const uint64_t*>(src + k0);
+        const uint32_t nb = len - k0 < 8u ? len - k0 : 8u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; k++) if (k < nb) d[k0 + k] = (uint8_t)(v >> (8 * k));
+    }
+}
+
 // get_atttention_mask helper on a flat id list
 __global__ void k_mask_flat(const int32_t* ids, int64_t n, int32_t pad, uint8_t* out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = ids[i] != pad;

@@ -179,7 +179,8 @@ int genztok_set_profiling(genztok_t *h, int on);
 int64_t genztok_profile_report(genztok_t *h, char *buf, int64_t cap, int reset);
 /* Engine knobs.  Sizing: "max_chunk_bytes" (before the first encode; sizes the word cache for its worst case),
  * "chunk_rows".  Pipeline selection and test knobs, all defaulting to the fastest correct setting: "no_flat" (1: fused row kernel
- * even where the byte-parallel pipeline applies), "no_tma" (store instructions instead of the TMA unit), "no_fixed_decode" (fixed-width rows through the any-rows decode kernels), "tma_columns" (staged
+ * even where the byte-parallel pipeline applies), "no_tma" (store instructions instead of the TMA unit), "no_fixed_decode" (fixed-width rows through the any-rows decode kernels),
+ * "no_token_decode" (ragged rows decoded by a warp per row instead of a thread per id), "tma_columns" (staged
  * columns per row, multiple of 16, 0 = from the text size), "no_side_pads", "flat_rows" (rows per tile of k_flat_rows, 1..32),
  * "rows_minb" / "words_minb" / "rows_grid" (occupancy of the pipeline's kernels), "group" (documents per tile of the fused
  * kernel, 0 = auto), "wide_rows", "grid_mult".  Unknown names are an error. */

@@ -320,6 +320,7 @@ def test_decode_pad_runs(tok, oracle):
     from genz_tokenize_b200 import Tokenize
     any_rows = Tokenize()
     any_rows.set_option("no_fixed_decode", 1)            # widths that are a multiple of 4 through the warp-per-row kernels too
+    any_rows.set_option("no_token_decode", 1)            # and ragged rows (a thread per id by default)
     for width in [1, 2, 3, 4, 7, 8, 9, 10, 11, 12, 16, 17, 31, 32, 33, 40, 64, 100, 124, 128, 132, 252, 255, 256, 257, 260, 300, 384, 516]:
         ids = _pad_run_rows(rng, 300, width, 0, 48423, exotic)
         ref = oracle.decode_batch(ids.reshape(-1), np.arange(0, 300 * width + 1, width, dtype=np.int64), threads=8)
@@ -332,7 +333,14 @@ def test_decode_pad_runs(tok, oracle):
     rows = [_pad_run_rows(rng, 1, int(w), 0, 48423, exotic)[0] for w in rng.integers(0, 200, 700)]
     off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
     flat = np.concatenate(rows).astype(np.int32)
-    assert tok.decode_batch(flat, off) == oracle.decode_batch(flat, off, threads=8)
+    ref = oracle.decode_batch(flat, off, threads=8)
+    assert tok.decode_batch(flat, off) == ref
+    assert any_rows.decode_batch(flat, off) == ref
+    sub = off[200:501]                                   # a batch whose offsets do not start at 0
+    assert tok.decode_batch(flat, sub) == ref[200:500]
+    assert any_rows.decode_batch(flat, sub) == ref[200:500]
+    empty = np.zeros(6, dtype=np.int64)                  # nothing but empty rows
+    assert tok.decode_batch(flat, empty) == [""] * 5
     # one very long row, mostly padding
     long_row = np.zeros((3, 70001), dtype=np.int32)
     long_row[:, :900] = rng.integers(0, 48423, (3, 900))
@@ -379,6 +387,24 @@ def test_decode_device_interleaved_batches(tok):
     assert lib.genztok_decode_device(h, 0, da.data_ptr(), None, 500, 64, oa.data_ptr(), xa.data_ptr(), None, st) == 0
     assert lib.genztok_decode_device(h, 0, db.data_ptr(), None, 500, 64, ob_.data_ptr(), xb.data_ptr(), None, st) == 0
     torch.cuda.synchronize()
+    # the same with ragged rows (decoded by id: the scan of A is overwritten by B's)
+    ra, rb = tok.encode_batch(["xin chào các bạn", "", "sinh_viên công_nghệ\n"] * 50), tok.encode_batch(["hello", "a b c d e f g"] * 70)
+    dev_t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    ia, fa, ib, fb = dev_t(ra["input_ids"]), dev_t(ra["row_off"]), dev_t(rb["input_ids"]), dev_t(rb["row_off"])
+    na, nb = len(ra["row_off"]) - 1, len(rb["row_off"]) - 1
+    qa, qb = torch.empty(na + 1, dtype=torch.int64, device=dev), torch.empty(nb + 1, dtype=torch.int64, device=dev)
+    sa, sb = C.c_int64(), C.c_int64()
+    assert lib.genztok_decode_device(h, 0, ia.data_ptr(), fa.data_ptr(), na, 0, qa.data_ptr(), None, C.byref(sa), st) == 0
+    assert lib.genztok_decode_device(h, 0, ib.data_ptr(), fb.data_ptr(), nb, 0, qb.data_ptr(), None, C.byref(sb), st) == 0
+    ya = torch.zeros(sa.value + 16, dtype=torch.uint8, device=dev)
+    yb = torch.zeros(sb.value + 16, dtype=torch.uint8, device=dev)
+    assert lib.genztok_decode_device(h, 0, ia.data_ptr(), fa.data_ptr(), na, 0, qa.data_ptr(), ya.data_ptr(), None, st) == 0
+    assert lib.genztok_decode_device(h, 0, ib.data_ptr(), fb.data_ptr(), nb, 0, qb.data_ptr(), yb.data_ptr(), None, st) == 0
+    torch.cuda.synchronize()
+    for enc, y, q, tot in [(ra, ya, qa, sa), (rb, yb, qb, sb)]:
+        raw, off = y.cpu().numpy().tobytes(), q.cpu().numpy()
+        assert off[-1] == tot.value and raw[tot.value:] == bytes(16)
+        assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(len(off) - 1)] == tok.decode_batch(enc["input_ids"], enc["row_off"])
     for ids, x, o, tot in [(a, xa, oa, ta), (b, xb, ob_, tb)]:
         raw, off = x.cpu().numpy().tobytes(), o.cpu().numpy()
         assert off[-1] == tot.value

@@ -33,3 +33,24 @@ for W in (128, 256):
     print("W=%d ms %.3f alg GB/s %.0f text MB %.0f" % (W, ms, alg / ms / 1e6, txt.numel() / 1e6), {k: round(v["ms"] / 5, 4) for k, v in prof.items()})
     import hashlib
     print("  sha", hashlib.sha256(txt[:1 << 24].cpu().numpy().tobytes()).hexdigest()[:16], int(off[-1].item()))
+
+# mask-trimmed ragged rows of the same sentences (BASELINE configs[3], the other way to hand the rows over): a thread per id,
+# and the warp-per-row kernels for comparison
+rag = tok.encode_batch((tb, to))
+r_ids, r_off = torch.from_numpy(rag["input_ids"]).to(dev), torch.from_numpy(rag["row_off"]).to(dev)
+for mode in (0, 1):
+    tok.set_option("no_token_decode", mode)
+    for _ in range(2):
+        txt, off = tok.decode_device(r_ids, r_off)
+    torch.cuda.synchronize()
+    tok.set_profiling(True); tok.profile_report(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in ev:
+        a.record(); txt, off = tok.decode_device(r_ids, r_off); b.record()
+    torch.cuda.synchronize()
+    prof = tok.profile_report(reset=True)
+    tok.set_profiling(False)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / 5
+    alg = 4 * int(r_ids.numel()) + int(txt.numel()) + 16 * n
+    print("ragged no_token_decode=%d ms %.3f alg GB/s %.0f ids %d text MB %.0f" % (mode, ms, alg / ms / 1e6, r_ids.numel(), txt.numel() / 1e6), {k: round(v["ms"] / 5, 4) for k, v in prof.items()})
+    print("  sha", hashlib.sha256(txt.cpu().numpy().tobytes()).hexdigest()[:16], int(off[-1].item()))
