@@ -142,8 +142,11 @@ int genztok_decode(genztok_t *h, const int32_t *ids, const int64_t *ids_off, int
                    genztok_text_t *out);
 void genztok_free_text(genztok_t *h, genztok_text_t *out);
 /* Device form: row byte lengths are produced first so that the caller can size `d_bytes`.
- * Step 1 (d_bytes == NULL): fills d_out_off[n+1] and returns the total in *total_bytes (synchronises).
- * Step 2: writes the text. */
+ * Step 1 (d_bytes == NULL): fills d_out_off[n+1] and returns the total in *total_bytes (synchronises; with ragged rows it
+ * also reads the two ends of d_ids_off).  Step 2: writes the text; d_bytes 16-byte aligned.  Step 1 leaves a per-row (or
+ * per-id) description in the handle for step 2 of the SAME batch (same pointers, n, width, on the same stream); a step 2
+ * for another batch redoes it.  Rows hold fewer than 2^31 ids.  With several devices in the handle, genztok_decode shards
+ * the rows across them. */
 int genztok_decode_device(genztok_t *h, int dev, const int32_t *d_ids, const int64_t *d_ids_off, int64_t n,
                           int32_t width, int64_t *d_out_off, uint8_t *d_bytes, int64_t *total_bytes, void *stream);
 
