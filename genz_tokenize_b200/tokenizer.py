@@ -485,8 +485,10 @@ class Tokenize(object):
         import torch
         return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream or 1)
 
-    def decode_device(self, d_ids, d_ids_off=None):
-        """Decode rows resident on the GPU: 2-D int32 tensor, or flat int32 + int64 offsets.  Returns (uint8 bytes, int64 offsets) tensors."""
+    def decode_device(self, d_ids, d_ids_off=None, out=None):
+        """Decode rows resident on the GPU: 2-D int32 tensor, or flat int32 + int64 offsets.  Returns (uint8 bytes, int64 offsets) tensors.
+        `out`: a uint8 CUDA tensor to write the text into when it is large enough (a reused ring for streamed batches); the
+        returned bytes are then a view of it."""
         import torch
         dev = d_ids.device
         if d_ids_off is None:
@@ -501,7 +503,8 @@ class Tokenize(object):
         rc = self._lib.genztok_decode_device(self._h, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
         if rc:
             self._err(rc, "genztok_decode_device")
-        out = torch.empty((max(total.value, 1),), dtype=torch.uint8, device=dev)
+        if out is None or out.numel() < max(total.value, 1) or out.device != dev or out.dtype != torch.uint8 or out.data_ptr() % 16:
+            out = torch.empty((max(total.value, 1),), dtype=torch.uint8, device=dev)
         rc = self._lib.genztok_decode_device(self._h, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), out.data_ptr(), None, st)
         if rc:
             self._err(rc, "genztok_decode_device")

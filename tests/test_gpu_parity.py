@@ -437,6 +437,12 @@ def test_device_api_matches_host_api(tok):
     texts = tok.decode_batch(host["input_ids"])
     raw, off = db.cpu().numpy().tobytes(), do.cpu().numpy()
     assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(5000)] == texts
+    ring = torch.zeros(int(db.numel()) + 4096, dtype=torch.uint8, device=dev)      # a caller-owned text buffer, reused
+    db2, do2 = tok.decode_device(out["input_ids"], out=ring)
+    assert db2.data_ptr() == ring.data_ptr() and torch.equal(db2, db) and torch.equal(do2, do) and int(ring[db.numel():].sum()) == 0
+    small = torch.zeros(16, dtype=torch.uint8, device=dev)                            # too small: a new tensor is returned
+    db3, _ = tok.decode_device(out["input_ids"], out=small)
+    assert db3.data_ptr() != small.data_ptr() and torch.equal(db3, db)
 
 
 def test_config2_full_size_properties(tok, oracle):

@@ -49,6 +49,7 @@ def main():
     pairs = tokens = in_bytes = dec_bytes = 0
     checksum = 0
     t_host = time.perf_counter()
+    txt_ring = None
     for k in range(n_chunks):
         g = k * world + rank                                             # global chunk index: shard by document, no collective
         m = min(n, args.pairs - k * n)
@@ -61,7 +62,9 @@ def main():
         tok.encode_device(d_t, d_to, d_p, d_po, max_len=W, out=o, text_bytes=len(tb), pair_bytes=len(pb))
         b.record()
         if not args.no_decode:
-            txt, toff = tok.decode_device(o["input_ids"])
+            txt, toff = tok.decode_device(o["input_ids"], out=txt_ring)
+            if txt_ring is None or txt_ring.numel() < txt.numel():       # the text ring: sized by the first chunk, with headroom
+                txt_ring = torch.empty((int(txt.numel() * 1.02) + (1 << 20),), dtype=torch.uint8, device=dev)
         c.record()
         torch.cuda.synchronize()
         if k > 0 or n_chunks == 1:                                       # the first chunk warms the word cache (cold BPE)
@@ -101,7 +104,7 @@ def main():
                 "decode_hbm_frac": dec_alg / (dec_ms * 1e-3) / 1e9 / (peak * world) if dec_ms else None,
                 "row_len_checksum": checksum, "host_seconds_total": host_s,
                 "note": "times are CUDA events around the device API calls, max over ranks; the first chunk of every rank (cold word cache) is run but not timed; "
-                        "decode time includes the allocation of the text tensor and one device->host read of its size per chunk"}
+                        "decode writes into a reused text ring (sized by the first chunk) and includes one device->host read of the text size per chunk"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
