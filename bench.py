@@ -389,6 +389,17 @@ def main():
                                               "best of %d passes (%.2f s each); single thread on the first %d documents (%.1f s)" % (n, threads, reps, dtN, n1, dt1)}
         except Exception as e:   # the baseline is reporting only; never fail the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": "failed: %r" % (e,)}
+        # The pure-Python reference itself cannot run here (its sources are not in this repository); what it did in the build
+        # container is on file (tools/time_python_reference.py) and quoted beside the port's numbers, marked as such.
+        try:
+            with open(os.path.join(ROOT, "profiles", "python_reference_container.json")) as f:
+                pr = json.loads(f.readline())
+            line["cpu_baseline"]["python_reference_recorded"] = {
+                "where": "build container (%d vCPU), not this host: recorded by tools/time_python_reference.py" % pr["cores"],
+                "single_process_tokens_per_s": pr["singles_128_single_process"]["tokens_per_s"],
+                "pool_tokens_per_s": pr["singles_128_pool"]["tokens_per_s"], "pool_workers": pr["singles_128_pool"]["workers"]}
+        except Exception:
+            pass
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
