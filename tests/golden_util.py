@@ -15,6 +15,12 @@ def load_golden():
         return json.loads(f.read().decode("ascii"))
 
 
+def load_decode_golden():
+    """Reference `decode` outputs on pad-run shaped rows (oracle/gen_golden_decode.py)."""
+    with gzip.open(os.path.join(HERE, "golden", "decode_v2.json.gz"), "rb") as f:
+        return json.loads(f.read().decode("ascii"))["blocks"]
+
+
 def _norm(out):
     if "offset" in out:
         out = dict(out)

@@ -62,3 +62,27 @@ def assert_matches_oracle(be, orc, eos_id=2, what=""):
         else:
             # without padding token_type_ids is the sequence_id list itself (tokenize.py:254-255)
             assert np.array_equal(orc["tt"], orc["seq"])
+
+
+def pad_run_rows(rng, n_rows, width, pad, vocab, exotic):
+    """Fixed-width id rows shaped like encoder output and unlike it: real ids, pad runs at the end / in the middle / at the
+    start, a non-pad last id behind a run, whole rows of pads, out-of-range ids."""
+    ids = np.full((n_rows, width), pad, dtype=np.int32)
+    for r in range(n_rows):
+        kind = rng.integers(0, 8)
+        nl = int(rng.integers(0, width + 1))
+        if kind == 0:
+            nl = 0
+        elif kind == 1:
+            nl = width
+        ids[r, :nl] = rng.integers(0, vocab, nl)
+        if kind == 2 and nl:                                  # pads inside the real part
+            k = rng.integers(0, nl, max(1, nl // 3))
+            ids[r, k] = pad
+        if kind == 3 and width:                               # something behind the run
+            ids[r, width - 1] = rng.integers(0, vocab)
+        if kind == 4 and width >= 3 and nl < width:                          # a second island in the run
+            ids[r, int(rng.integers(nl, width))] = rng.integers(0, vocab)
+        if kind == 5 and nl:
+            ids[r, rng.integers(0, nl)] = exotic[rng.integers(0, len(exotic))]
+    return ids

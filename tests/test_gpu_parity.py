@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from golden_util import check_cases
-from parity_util import assert_matches_oracle
+from parity_util import assert_matches_oracle, pad_run_rows as _pad_run_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -288,30 +288,6 @@ def test_decode_roundtrip_batch(tok, oracle):
     assert tok.decode_batch(big["input_ids"]) == oracle.decode_batch(big["input_ids"].reshape(-1), np.arange(0, 30000 * 16 + 1, 16, dtype=np.int64), threads=8)
 
 
-def _pad_run_rows(rng, n_rows, width, pad, vocab, exotic):
-    """Fixed-width id rows shaped like encoder output and unlike it: real ids, pad runs at the end / in the middle / at the
-    start, a non-pad last id behind a run, whole rows of pads, out-of-range ids."""
-    ids = np.full((n_rows, width), pad, dtype=np.int32)
-    for r in range(n_rows):
-        kind = rng.integers(0, 8)
-        nl = int(rng.integers(0, width + 1))
-        if kind == 0:
-            nl = 0
-        elif kind == 1:
-            nl = width
-        ids[r, :nl] = rng.integers(0, vocab, nl)
-        if kind == 2 and nl:                                  # pads inside the real part
-            k = rng.integers(0, nl, max(1, nl // 3))
-            ids[r, k] = pad
-        if kind == 3 and width:                               # something behind the run
-            ids[r, width - 1] = rng.integers(0, vocab)
-        if kind == 4 and width >= 3 and nl < width:                          # a second island in the run
-            ids[r, int(rng.integers(nl, width))] = rng.integers(0, vocab)
-        if kind == 5 and nl:
-            ids[r, rng.integers(0, nl)] = exotic[rng.integers(0, len(exotic))]
-    return ids
-
-
 def test_decode_pad_runs(tok, oracle):
     # the write pass sends the trailing run of pad ids and the last piece straight to global memory: every width around the
     # 16-byte units and the 32-id batches, every shape of row, against the oracle
@@ -365,6 +341,27 @@ def test_decode_pad_runs_custom_pad_tokens():
         for width in [5, 16, 37, 128, 260]:
             ids = _pad_run_rows(rng, 200, width, pad, t.vocab_size(), [-1, 10**6, 1, 2, 0])
             assert t.decode_batch(ids) == o.decode_batch(ids.reshape(-1), np.arange(0, 200 * width + 1, width, dtype=np.int64)), (pad_tok, width)
+
+
+def test_decode_pad_run_vectors_from_the_reference():
+    # the same shapes against what the reference's decode() printed (tests/golden/decode_v2.json.gz), through all three
+    # kernel families: fixed-width (default), warp per row, and -- as ragged rows -- a thread per id
+    from genz_tokenize_b200 import Tokenize
+    from golden_util import load_decode_golden
+    toks = {}
+    for b in load_decode_golden():
+        if b["pad_token"] not in toks:
+            sp = [b["pad_token"], "<s>", "</s>", "<mask>", "<unk>"]
+            t, a = Tokenize(*sp), Tokenize(*sp)
+            a.set_option("no_fixed_decode", 1)
+            assert t.encoder[b["pad_token"]] == b["pad_id"]
+            toks[b["pad_token"]] = (t, a)
+        t, a = toks[b["pad_token"]]
+        ids = np.array(b["ids"], dtype=np.int64).astype(np.int32)
+        n, w = ids.shape
+        assert t.decode_batch(ids) == b["out"], (b["pad_token"], w)
+        assert a.decode_batch(ids) == b["out"], (b["pad_token"], w)
+        assert t.decode_batch(ids.reshape(-1), np.arange(0, n * w + 1, w, dtype=np.int64)) == b["out"], (b["pad_token"], w)
 
 
 def test_decode_device_interleaved_batches(tok):

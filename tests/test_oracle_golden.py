@@ -3,6 +3,7 @@ import hashlib
 import os
 import tempfile
 
+import numpy as np
 import pytest
 
 from golden_util import check_cases
@@ -91,6 +92,19 @@ def test_sequence_id_state_machine(oracle, golden):
 def test_decode(oracle, golden):
     for c in golden["decode"]:
         assert oracle.decode(c["ids"]) == c["out"], c["ids"]
+
+
+def test_decode_pad_run_vectors():
+    # reference decode() of rows with trailing / inner / leading pad runs, for pad tokens of every text length
+    from golden_util import load_decode_golden
+    from oracle.oracle import Oracle
+    cache = {}
+    for b in load_decode_golden():
+        sp = [b["pad_token"], "<s>", "</s>", "<mask>", "<unk>"]
+        o = cache.setdefault(b["pad_token"], Oracle(specials=sp))
+        ids = np.array(b["ids"], dtype=np.int64).astype(np.int32)
+        n, w = ids.shape
+        assert o.decode_batch(ids.reshape(-1), np.arange(0, n * w + 1, w, dtype=np.int64)) == b["out"], (b["pad_token"], w)
 
 
 def test_loader_quirks(golden):
