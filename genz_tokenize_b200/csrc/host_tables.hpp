@@ -122,7 +122,7 @@ struct HostTables {
         out->reserve(raw.size());
         const uint8_t* p = (const uint8_t*)raw.data();
         for (size_t i = 0; i < raw.size();) {
-            uint32_t cp;
+            uint32_t cp = 0;
             int l = utf8_decode(p + i, raw.size() - i, &cp);
             if (l == 0) {
                 char m[256];
@@ -145,14 +145,14 @@ struct HostTables {
     static void strip_ws(const uint8_t* p, size_t n, size_t* b, size_t* e) {
         size_t s = 0, t = n;
         while (s < t) {
-            uint32_t cp; int l = utf8_decode(p + s, t - s, &cp);
+            uint32_t cp = 0; int l = utf8_decode(p + s, t - s, &cp);
             if (l == 0 || !is_space_cp(cp)) break;
             s += (size_t)l;
         }
         while (t > s) {
             size_t k = t - 1;
             while (k > s && (p[k] & 0xC0) == 0x80) k--;
-            uint32_t cp; int l = utf8_decode(p + k, t - k, &cp);
+            uint32_t cp = 0; int l = utf8_decode(p + k, t - k, &cp);
             if (l == 0 || !is_space_cp(cp)) break;
             t = k;
         }
@@ -186,7 +186,7 @@ struct HostTables {
         const uint8_t* p = (const uint8_t*)line.data();
         size_t k = 0, n = line.size();
         while (k < n) {
-            uint32_t cp; int l = utf8_decode(p + k, n - k, &cp);
+            uint32_t cp = 0; int l = utf8_decode(p + k, n - k, &cp);
             if (l == 0) l = 1;
             if (is_space_cp(cp)) { k += (size_t)l; continue; }
             size_t s = k;
@@ -229,7 +229,7 @@ struct HostTables {
     static void append_cp_set(const std::string& s, std::vector<uint32_t>* cps) {
         const uint8_t* p = (const uint8_t*)s.data();
         for (size_t i = 0; i < s.size();) {
-            uint32_t cp; int l = utf8_decode(p + i, s.size() - i, &cp);
+            uint32_t cp = 0; int l = utf8_decode(p + i, s.size() - i, &cp);
             if (l == 0) { i++; continue; }
             cps->push_back(cp);
             i += (size_t)l;
