@@ -7,6 +7,8 @@ include/genztok.h); this package is the thin ctypes wrapper plus the synthetic-w
 generator used by the benchmark.  There is no CPU fallback.
 """
 from . import preprocess
+from .collection import DataCollection
+from .stream import iter_line_batches
 from .tokenizer import BatchEncoding, GenztokError, Tokenize, pack_strings
 
-__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings", "preprocess"]
+__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings", "preprocess", "DataCollection", "iter_line_batches"]

@@ -442,6 +442,34 @@ def test_device_api_matches_host_api(tok):
     assert db3.data_ptr() != small.data_ptr() and torch.equal(db3, db)
 
 
+def test_file_to_device_batches_handoff(tok, oracle):
+    # SURVEY.md 8 f4, both sides of the path: lines of a file -> packed batches -> planes on the GPU -> shuffled batches
+    import torch
+    from genz_tokenize_b200 import DataCollection, iter_line_batches, workload
+    tb, to = workload.generate(811, 3000, 0, 13, 0.0)
+    raw = tb.tobytes()
+    lines = [raw[to[i]:to[i + 1]].decode("utf-8") for i in range(3000)]
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "docs.txt")
+        open(p, "wb").write(("\n".join(lines) + "\n").encode("utf-8"))
+        rows = []
+        for b, o in iter_line_batches(p, docs_per_batch=1024, read_bytes=50000):
+            rows.append(tok.encode_batch((b, o), max_len=32)["input_ids"].copy())
+    ids = np.concatenate(rows)
+    ref = oracle.encode_batch((tb, to), None, threads=8, max_len=32)
+    assert np.array_equal(ids.reshape(-1), ref["ids"])
+    dev = torch.device("cuda:0")
+    pad16 = lambda a: torch.from_numpy(np.concatenate([a, np.zeros((-len(a)) % 16 + 16, dtype=np.uint8)])).to(dev)
+    out = tok.encode_device(pad16(tb), torch.from_numpy(to).to(dev), max_len=32, text_bytes=len(tb))
+    y = torch.arange(3000, device=dev)
+    dc = DataCollection.from_encoding(out, y)
+    got = torch.empty((3000, 32), dtype=torch.int32, device=dev)
+    for feats, yy in dc.to_torch_batches(batch_size=256, seed=1):
+        assert feats["input_ids"].is_cuda and feats["attention_mask"].is_cuda and yy.is_cuda
+        got[yy] = feats["input_ids"]
+    assert np.array_equal(got.cpu().numpy(), ids)
+
+
 def test_config2_full_size_properties(tok, oracle):
     # BASELINE.json configs[1]: 1M single sentences, max_len=128 -- first 100k rows against the oracle, the whole
     # batch through size-independent properties (row framing, mask == non-pad, decode/encode idempotence on a sample)
