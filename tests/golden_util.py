@@ -44,3 +44,26 @@ def check_case(tok, c, where=""):
 def check_cases(tok, cases, where=""):
     for i, c in enumerate(cases):
         check_case(tok, c, "%s[%d]" % (where, i))
+
+
+# ---- digests over many rows: pins tens of thousands of reference rows without storing them -------------------------
+def row_bytes(status, ids=None, mask=None, seq=None, tt=None):
+    """Canonical bytes of one encoded row: b"E" for a row on which the reference raises ValueError, else b"R" followed by,
+    per field, an int32 length and the values (input_ids int32, attention_mask uint8, sequence_id / token_type_ids int8 with
+    None as -1; the last two only for pairs)."""
+    import numpy as np
+    if status:
+        return b"E"
+    out = [b"R"]
+    for v, dt in ((ids, np.int32), (mask, np.uint8), (seq, np.int8), (tt, np.int8)):
+        if v is None:
+            continue
+        a = np.asarray([(-1 if x is None else x) for x in v] if isinstance(v, list) else v).astype(dt)
+        out.append(np.int32(len(a)).tobytes())
+        out.append(a.tobytes())
+    return b"".join(out)
+
+
+def load_encode_digests():
+    with open(os.path.join(HERE, "golden", "encode_digest_v1.json"), "r") as f:
+        return json.load(f)["configs"]

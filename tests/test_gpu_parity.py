@@ -69,6 +69,28 @@ def test_random_rows_batch(tok, golden):
                 assert be.row(i) == exp, (blk["gen"], i, blk["texts"][i], blk["pairs"][i] if blk["pairs"] else None)
 
 
+def test_encode_digests_85k_reference_rows(tok):
+    # the CUDA path against the reference itself (no oracle in between): SHA-256 over every row's reference dict on 85,000
+    # seeded rows -- BASELINE-shaped batches, noisy / heavily truncated (ValueError rows) / ragged / unpadded regimes
+    from genz_tokenize_b200 import workload
+    from golden_util import load_encode_digests, row_bytes
+    for c in load_encode_digests():
+        t = workload.generate(c["seed"], c["n"], c["lo"], c["hi"], c["noise"])
+        p = workload.generate(c["seed"] + 1000, c["n"], c["lo"], c["hi"], c["noise"]) if c["paired"] else None
+        be = tok.encode_batch(t, p, **c["kw"])
+        h, errors = hashlib.sha256(), 0
+        for i in range(c["n"]):
+            try:
+                r = be.row(i)
+            except ValueError:
+                h.update(row_bytes(1))
+                errors += 1
+                continue
+            h.update(row_bytes(0, r["input_ids"], r["attention_mask"], r.get("sequence_id"), r.get("token_type_ids")))
+        assert errors == c["value_errors"], c
+        assert h.hexdigest() == c["sha256"], c
+
+
 def test_bpe_strings(tok, golden):
     for c in golden["bpe"]:
         assert tok.bpe(c["w"]) == c["out"], c["w"]

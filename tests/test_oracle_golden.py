@@ -107,6 +107,33 @@ def test_decode_pad_run_vectors():
         assert o.decode_batch(ids.reshape(-1), np.arange(0, n * w + 1, w, dtype=np.int64)) == b["out"], (b["pad_token"], w)
 
 
+def _oracle_digest(orc, paired):
+    from golden_util import row_bytes
+    h = hashlib.sha256()
+    io, so, to = orc["ids_off"], orc.get("seq_off"), orc.get("tt_off")
+    for i in range(orc["n"]):
+        if orc["status"][i]:
+            h.update(row_bytes(1))
+            continue
+        a, b = io[i], io[i + 1]
+        h.update(row_bytes(0, orc["ids"][a:b], orc["mask"][a:b],
+                           orc["seq"][so[i]:so[i + 1]] if paired else None, orc["tt"][to[i]:to[i + 1]] if paired else None))
+    return h.hexdigest()
+
+
+def test_encode_digests_85k_reference_rows(oracle):
+    # SHA-256 over the reference's outputs on 85,000 seeded rows (oracle/gen_golden_digest.py): BASELINE-shaped batches plus
+    # noisy, heavily truncated (4,001 ValueError rows), ragged and unpadded regimes
+    from genz_tokenize_b200 import workload
+    from golden_util import load_encode_digests
+    for c in load_encode_digests():
+        t = workload.generate(c["seed"], c["n"], c["lo"], c["hi"], c["noise"])
+        p = workload.generate(c["seed"] + 1000, c["n"], c["lo"], c["hi"], c["noise"]) if c["paired"] else None
+        orc = oracle.encode_batch(t, p, threads=8, **c["kw"])
+        assert int(orc["status"].sum()) == c["value_errors"], c
+        assert _oracle_digest(orc, c["paired"]) == c["sha256"], c
+
+
 def test_loader_quirks(golden):
     from oracle.oracle import Oracle
     with tempfile.TemporaryDirectory() as td:
