@@ -40,7 +40,7 @@ def main():
     for c in CONFIGS:
         ts = workload.unpack(*workload.generate(c["seed"], c["n"], c["lo"], c["hi"], c["noise"], wl))
         ps = workload.unpack(*workload.generate(c["seed"] + 1000, c["n"], c["lo"], c["hi"], c["noise"], wl)) if c["paired"] else [None] * c["n"]
-        h = hashlib.sha256()
+        h, hd = hashlib.sha256(), hashlib.sha256()             # hd: decode() of every row's input_ids (tokenize.py:137-139)
         errors = 0
         for t, p in zip(ts, ps):
             try:
@@ -50,7 +50,8 @@ def main():
                 errors += 1
                 continue
             h.update(row_bytes(0, r["input_ids"], r["attention_mask"], r.get("sequence_id"), r.get("token_type_ids")))
-        out.append(dict(c, sha256=h.hexdigest(), value_errors=errors))
+            hd.update(tok.decode(r["input_ids"]).encode("utf-8", "surrogatepass") + b"\n")
+        out.append(dict(c, sha256=h.hexdigest(), value_errors=errors, decode_sha256=hd.hexdigest()))
         print(c["seed"], c["n"], c["kw"], h.hexdigest()[:16], "errors", errors, flush=True)
     path = os.path.join(ROOT, "tests", "golden", "encode_digest_v1.json")
     with open(path, "w") as f:

@@ -89,6 +89,14 @@ def test_encode_digests_85k_reference_rows(tok):
             h.update(row_bytes(0, r["input_ids"], r["attention_mask"], r.get("sequence_id"), r.get("token_type_ids")))
         assert errors == c["value_errors"], c
         assert h.hexdigest() == c["sha256"], c
+        # and decode() of those rows: fixed planes through the fixed-width kernels, ragged ones a thread per id
+        texts = tok.decode_batch(be["input_ids"]) if be["input_ids"].ndim == 2 else tok.decode_batch(be["input_ids"], be["row_off"])
+        hd = hashlib.sha256()
+        ok = (be["row_status"] == 0) if "row_status" in be else np.ones(c["n"], dtype=bool)    # rows the reference raised on have no ids
+        for i, s in enumerate(texts):
+            if ok[i]:
+                hd.update(s.encode("utf-8", "surrogatepass") + b"\n")
+        assert hd.hexdigest() == c["decode_sha256"], c
 
 
 def test_bpe_strings(tok, golden):

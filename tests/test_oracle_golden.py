@@ -132,6 +132,13 @@ def test_encode_digests_85k_reference_rows(oracle):
         orc = oracle.encode_batch(t, p, threads=8, **c["kw"])
         assert int(orc["status"].sum()) == c["value_errors"], c
         assert _oracle_digest(orc, c["paired"]) == c["sha256"], c
+        # decode() of every row the reference returned (rows it raised on have no ids to decode)
+        texts = oracle.decode_batch(orc["ids"], orc["ids_off"], threads=8)
+        hd = hashlib.sha256()
+        for i, s in enumerate(texts):
+            if not orc["status"][i]:
+                hd.update(s.encode("utf-8", "surrogatepass") + b"\n")
+        assert hd.hexdigest() == c["decode_sha256"], c
 
 
 def test_loader_quirks(golden):
