@@ -67,6 +67,10 @@ SIGNATURES = {
     "genztok_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "genztok_profile_report": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int]),
     "genztok_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "genztok_check_errors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
+    "genztok_synth_init": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
+    "genztok_synth_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "genztok_digest_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

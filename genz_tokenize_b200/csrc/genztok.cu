@@ -32,6 +32,7 @@
 #include "host_tables.hpp"
 #include "post.cuh"
 #include "prep.cuh"
+#include "synth.cuh"
 
 using namespace gzt;
 
@@ -54,7 +55,7 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct ProfEvent { int name; cudaEvent_t a, b; };
+struct ProfEvent { int name; cudaEvent_t a, b; int64_t alg; };
 
 struct DeviceCtx {
     int device = 0;
@@ -76,6 +77,15 @@ struct DeviceCtx {
     int64_t tok_base = 0, tok_n = -1;             // the ids that scan describes
     struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; int by_id = 0; } dec_sig;   // the batch it describes
     struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok, fixa, fixp; } flat[2];   // byte-parallel pipeline, per side
+    // the shared work areas (word cache, lists, flat arrays) are used by one stream at a time: a call on another stream
+    // first waits for the event the previous call left behind
+    cudaEvent_t last_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false;
+    // synthetic workload generator (synth.cuh): tables and the length scratch
+    SynthTables synth{};
+    bool synth_ready = false;
+    DevBuf synth_len;
     // profiling
     bool profiling = false;
     std::vector<ProfEvent> events;
@@ -107,7 +117,8 @@ struct genztok {
     int64_t no_fixed_decode = 0;         // decode fixed-width rows with the any-rows kernels (test knob)
     int64_t force_kr = 0;                // staged columns per row of the TMA write-out (test knob; 0 = from the text size)
     std::vector<std::string> prof_names;
-    std::map<std::string, std::pair<int64_t, double>> prof_acc;
+    struct ProfAcc { int64_t launches = 0; double ms = 0; int64_t alg = 0; };
+    std::map<std::string, ProfAcc> prof_acc;
     // pinned host pool
     std::multimap<size_t, void*> host_pool;
     size_t host_pool_bytes = 0;
@@ -140,11 +151,13 @@ int prof_name_id(genztok_t* h, const char* name) {
 
 struct LaunchScope {   // counts the launch and, when profiling, brackets it with events on the stream
     genztok_t* h; DeviceCtx* d; ProfEvent ev{}; bool on;
-    LaunchScope(genztok_t* h_, DeviceCtx* d_, const char* name) : h(h_), d(d_), on(d_->profiling) {
+    // alg_bytes: the algorithmic bytes of this launch (SURVEY.md 8 d4 split by kernel), reported next to its time
+    LaunchScope(genztok_t* h_, DeviceCtx* d_, const char* name, int64_t alg_bytes = 0) : h(h_), d(d_), on(d_->profiling) {
         h->launches++;
         dbg_name = name;
         if (on) {
             ev.name = prof_name_id(h, name);
+            ev.alg = alg_bytes;
             for (cudaEvent_t* e : {&ev.a, &ev.b}) {
                 if (!d->free_events.empty()) { *e = d->free_events.back(); d->free_events.pop_back(); }
                 else cudaEventCreate(e);
@@ -221,9 +234,22 @@ int init_device(genztok_t* h, DeviceCtx* d) {
     return GENZTOK_OK;
 }
 
+// Calls that use the device context's shared work areas on different streams are ordered by an event (the word cache, the
+// redo / fix lists and the flat arrays belong to one call at a time).
+int stream_enter(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
+    if (d->last_valid && d->last_stream != st) CU(cudaStreamWaitEvent(st, d->last_done, 0));
+    return GENZTOK_OK;
+}
+int stream_leave(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
+    if (!d->last_done) CU(cudaEventCreateWithFlags(&d->last_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(d->last_done, st));
+    d->last_stream = st; d->last_valid = true;
+    return GENZTOK_OK;
+}
+
 uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
-int ensure_cache(genztok_t* h, DeviceCtx* d) {
+int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     if (d->cache_ready) return GENZTOK_OK;
     const uint64_t B = (uint64_t)h->max_chunk_bytes;
     const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
@@ -232,8 +258,9 @@ int ensure_cache(genztok_t* h, DeviceCtx* d) {
     CU(d->tok_arena.ensure((2 * B + 64) * 4));
     CU(d->pending.ensure((B / 2 + 64) * 4));
     CU(d->ctr.ensure(C_COUNT * 8));
-    CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), d->stream));
-    CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, d->stream));
+    // on the stream that runs the kernels of this call (the handle's own stream is non-blocking: nothing else orders it with the caller's)
+    CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), st));
+    CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, st));
     WordCache& C = d->C;
     C.slots = d->slots.as<Slot>(); C.mask = (uint32_t)(slots - 1);
     C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + 64;
@@ -417,7 +444,9 @@ int flat_side_setup(genztok_t* h, DeviceCtx* d, int s, const Side& side, int64_t
 int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Side& a, const Side* b, int64_t n, int32_t W, uint32_t flags,
                            const genztok_dev_planes_t& P) {
     LaunchScope::cur_stream = st;
-    int rc = ensure_cache(h, d);
+    int rc = stream_enter(h, d, st);
+    if (rc) return rc;
+    rc = ensure_cache(h, d, st);
     if (rc) return rc;
     const int64_t bytes = a.nbytes + (b ? b->nbytes : 0);
     if (bytes > h->max_chunk_bytes) return fail(h, GENZTOK_E_LIMIT, "chunk of %lld bytes exceeds max_chunk_bytes=%lld", (long long)bytes, (long long)h->max_chunk_bytes);
@@ -479,10 +508,12 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             static const TmaPlanes no_planes{};
             for (int s = 0; s < (b ? 2 : 1); s++) {
                 const FlatSide& S = s ? F.b : F.a;
-                LaunchScope ls(h, d, "k_flat_words");
                 const bool pads = J.on != 0;                          // every launch takes its share of the pad tiles
                 PadJob Js = J;
                 if (b) { const int32_t half = J.n_tiles / 2; Js.tile0 = s ? half : 0; Js.n_tiles = s ? J.n_tiles - half : half; }
+                // algorithmic bytes: this side's text, and the pad columns it stores on the side (rows x (W - KR) x (4 + 1 [+ 1]))
+                const int64_t pad_rows = pads ? std::min<int64_t>(n - (int64_t)Js.tile0 * 32, (int64_t)Js.n_tiles * 32) : 0;
+                LaunchScope ls(h, d, "k_flat_words", (s ? b->nbytes : a.nbytes) + pad_rows * (int64_t)(W - J.KR) * (5 + J.want_tt));
                 const size_t dsm = pads ? tma_const_bytes(J.D, J.PB) : 0;
                 auto wk = h->words_minb == 3 ? k_flat_words<3, 2> : (h->words_minb == 14 ? k_flat_words<4, 2> : (h->words_minb == 5 ? k_flat_words<5, 1> : k_flat_words<4, 1>));
                 const int64_t wmb = h->words_minb == 14 ? 4 : h->words_minb;
@@ -503,7 +534,6 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             {
                 const bool tt = F.has_pair && F.tt;
                 const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * (r128(sizeof(FlatTile)) + r128((size_t)M.KR * 4));
-                (void)tt;
                 // (the pair instantiation needs its 63 registers: 4 blocks per SM unless asked otherwise)
                 auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 15 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
                                        : (h->rows_minb == 8 ? k_flat_rows<8, false> : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>)));
@@ -514,7 +544,8 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 const int64_t tiles = (n + F.D - 1) / F.D;
                 if (h->rows_grid > 0) occ = std::min<int>(occ, (int)h->rows_grid);
                 const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)d->sm_count * occ * h->grid_mult));
-                LaunchScope ls(h, d, "k_flat_rows");
+                // algorithmic bytes: the document offsets in, the staged columns (and, without the side job, the pad columns) of every plane out
+                LaunchScope ls(h, d, "k_flat_rows", (int64_t)(b ? 2 : 1) * 8 * (n + 1) + n * (int64_t)(M.PB ? W : M.KR) * (5 + (tt ? 1 : 0)));
                 CU(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, d->T, d->C, F, M));
             }
             CU(cudaGetLastError());
@@ -542,7 +573,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         k_post_rows<<<d->sm_count, 256, 0, st>>>(d->T, Q, d->C.ctr + C_FIX);
         CU(cudaGetLastError());
     }
-    return GENZTOK_OK;
+    return stream_leave(h, d, st);
 }
 
 void* host_pool_get(genztok_t* h, size_t bytes) {
@@ -622,6 +653,9 @@ void genztok_destroy(genztok_t* h) {
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : d->free_events) cudaEventDestroy(e);
+        if (d->last_done) cudaEventDestroy(d->last_done);
+        d->synth_len.release();
+        for (auto& fb : d->flat) for (DevBuf* b : {&fb.dsb, &fb.st, &fb.tpref, &fb.cnt, &fb.wtok, &fb.fixa, &fb.fixp}) b->release();
         if (d->stream) cudaStreamDestroy(d->stream);
         delete d;
     }
@@ -744,7 +778,7 @@ int64_t genztok_profile_report(genztok_t* h, char* buf, int64_t cap, int reset) 
             float ms = 0;
             if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
                 auto& acc = h->prof_acc[h->prof_names[(size_t)e.name]];
-                acc.first += 1; acc.second += ms;
+                acc.launches += 1; acc.ms += ms; acc.alg += e.alg;
             } else cudaGetLastError();
             d->free_events.push_back(e.a); d->free_events.push_back(e.b);
         }
@@ -754,7 +788,8 @@ int64_t genztok_profile_report(genztok_t* h, char* buf, int64_t cap, int reset) 
     bool first = true;
     for (auto& kv : h->prof_acc) {
         char t[256];
-        snprintf(t, sizeof t, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+        snprintf(t, sizeof t, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"alg_bytes\": %lld}", first ? "" : ", ", kv.first.c_str(), (long long)kv.second.launches,
+                 kv.second.ms, (long long)kv.second.alg);
         s += t; first = false;
     }
     s += "}";
@@ -846,7 +881,7 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
             r0 = r1;
         }
     }
-    FAIL_RC(ensure_cache(h, d));
+    FAIL_RC(ensure_cache(h, d, st));
     unsigned long long tokens_before = 0;
     CUF(cudaMemcpyAsync(&tokens_before, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaStreamSynchronize(st));
@@ -1110,11 +1145,21 @@ extern "C" {
 namespace {
 
 // Both passes of the decode on one device; the caller holds h->mu (or owns the device context, as the workers of genztok_decode do).
+int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st);
 int decode_on_device(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
                      uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
     CU(cudaSetDevice(d->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     LaunchScope::cur_stream = st;
+    int rc = stream_enter(h, d, st);
+    if (rc) return rc;
+    rc = decode_on_device_impl(h, d, d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, st);
+    if (rc) return rc;
+    return stream_leave(h, d, st);
+}
+int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st) {
     DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes, nullptr};
     // fixed-width rows of whole 16-byte vectors whose byte counts fit 32 bits: a warp per 32 rows instead of a warp per row
     const bool fixed = !d_ids_off && width >= 4 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ids) & 15) == 0 &&
@@ -1373,6 +1418,94 @@ int genztok_preprocess(genztok_t* h, int op, const uint8_t* text, const int64_t*
     ob->mallocs.push_back(bytes);
     out->n = n; out->total = total_all; out->bytes = bytes; out->off = off; out->_owner = ob;
     return GENZTOK_OK;
+}
+
+// ---- measurement plumbing: synthetic workload on the device, plane digest, error counter (synth.cuh) ---------------
+int genztok_synth_init(genztok_t* h, int dev, const uint8_t* wblob, int64_t wblob_len, const uint32_t* wstart, const uint32_t* wlen, const uint32_t* cdf32,
+                       int64_t nw, const uint8_t* eblob, int64_t eblob_len, const uint32_t* estart, const uint32_t* elen, int64_t ne) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (!wblob || !wstart || !wlen || !cdf32 || nw < 1 || !eblob || !estart || !elen || ne < 1) return fail(h, GENZTOK_E_INVALID, "genztok_synth_init: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    SynthTables& S = d->synth;
+    CU(upload(d, std::vector<uint8_t>(wblob, wblob + wblob_len), &S.wblob));
+    CU(upload(d, std::vector<uint32_t>(wstart, wstart + nw), &S.wstart));
+    CU(upload(d, std::vector<uint32_t>(wlen, wlen + nw), &S.wlen));
+    CU(upload(d, std::vector<uint32_t>(cdf32, cdf32 + nw), &S.cdf32));
+    CU(upload(d, std::vector<uint8_t>(eblob, eblob + eblob_len), &S.eblob));
+    CU(upload(d, std::vector<uint32_t>(estart, estart + ne), &S.estart));
+    CU(upload(d, std::vector<uint32_t>(elen, elen + ne), &S.elen));
+    S.nw = (uint32_t)nw; S.ne = (uint32_t)ne;
+    d->synth_ready = true;
+    return GENZTOK_OK;
+}
+
+int genztok_synth_device(genztok_t* h, int dev, uint64_t seed, int64_t doc0, int64_t n, int side, int lo, int hi, uint32_t noise_thr, int64_t* d_off,
+                         uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_off || lo < 0 || hi < lo || hi > 4096) return fail(h, GENZTOK_E_INVALID, "genztok_synth_device: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    if (!d->synth_ready) return fail(h, GENZTOK_E_INVALID, "genztok_synth_device: call genztok_synth_init first");
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    LaunchScope::cur_stream = st;
+    SynthArgs A{seed, doc0, n, side, lo, hi, noise_thr, nullptr, d_off, d_bytes};
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * 16));
+    if (!d_bytes) {
+        CU(d->synth_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
+        A.len_out = d->synth_len.as<int64_t>();
+        if (n > 0) { LaunchScope ls(h, d, "k_synth_len"); k_synth<false><<<grid, 256, 0, st>>>(d->synth, A); }
+        int rc = launch_scan(h, d, st, d->synth_len.as<int64_t>(), d_off, n);
+        if (rc) return rc;
+        if (total_bytes) {
+            CU(cudaMemcpyAsync(total_bytes, d_off + n, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return GENZTOK_OK;
+    }
+    if (n > 0) { LaunchScope ls(h, d, "k_synth_write"); k_synth<true><<<grid, 256, 0, st>>>(d->synth, A); }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+int genztok_digest_device(genztok_t* h, int dev, const int32_t* d_ids, const uint8_t* d_mask, const int8_t* d_tt, int64_t n, int32_t width, int64_t row0,
+                          uint64_t* d_acc, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_ids || !d_mask || !d_acc || width < 4 || (width & 3)) return fail(h, GENZTOK_E_INVALID, "genztok_digest_device: needs ids, mask and a width that is a multiple of 4");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    LaunchScope::cur_stream = st;
+    DigestArgs A{reinterpret_cast<const uint32_t*>(d_ids), reinterpret_cast<const uint32_t*>(d_mask), reinterpret_cast<const uint32_t*>(d_tt), n, row0, width,
+                 reinterpret_cast<unsigned long long*>(d_acc)};
+    if (n > 0) { LaunchScope ls(h, d, "k_plane_digest"); k_plane_digest<<<(unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 8), 256, 0, st>>>(A); }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
+/* The device pipeline counts inconsistencies (offsets outside the stated text, exhausted work lists) instead of faulting; the
+ * host path checks the counter after every call, the asynchronous device path leaves that to the caller: this reads it
+ * (synchronises `stream`). */
+int genztok_check_errors(genztok_t* h, int dev, void* stream, int64_t* n_errors) {
+    if (!h || !n_errors) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    *n_errors = 0;
+    if (!d->cache_ready) return GENZTOK_OK;
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    unsigned long long nerr = 0;
+    CU(cudaMemcpyAsync(&nerr, d->C.ctr + C_ERR, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_errors = (int64_t)nerr;
+    return nerr ? fail(h, GENZTOK_E_CUDA, "device pipeline reported %llu inconsistencies", nerr) : GENZTOK_OK;
 }
 
 // ---- helpers ----------------------------------------------------------------------------------------------

@@ -510,6 +510,55 @@ class Tokenize(object):
             self._err(rc, "genztok_decode_device")
         return out[:total.value], out_off
 
+    # ---- measurement plumbing (bench.py, tests): synthetic workload on the device, plane digest, error counter -----------
+    def synth_device(self, seed, doc0, n, side=0, lo=3, hi=13, noise=0.0, device=None):
+        """Documents [doc0, doc0 + n) of workload.generate_hashed produced on the GPU: (uint8 bytes padded for 16-byte loads,
+        int64 offsets[n+1], byte count)."""
+        import torch
+        from . import workload
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if not getattr(self, "_synth_ready", False):
+            T = workload.default_synth_tables()
+            keep = [np.ascontiguousarray(a) for a in (T.wblob, T.wstart, T.wlen, T.cdf32, T.eblob, T.estart, T.elen)]
+            rc = self._lib.genztok_synth_init(self._h, 0, keep[0].ctypes.data, len(keep[0]), keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, T.nw,
+                                              keep[4].ctypes.data, len(keep[4]), keep[5].ctypes.data, keep[6].ctypes.data, T.ne)
+            if rc:
+                self._err(rc, "genztok_synth_init")
+            self._synth_ready = True
+        st = self._torch_stream(dev)
+        off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+        total = C.c_int64()
+        thr = workload.noise_threshold(noise)
+        rc = self._lib.genztok_synth_device(self._h, 0, int(seed), int(doc0), int(n), int(side), int(lo), int(hi), thr, off.data_ptr(), None, C.byref(total), st)
+        if rc:
+            self._err(rc, "genztok_synth_device")
+        nb = int(total.value)
+        data = torch.zeros((nb + (-nb) % 16 + 32,), dtype=torch.uint8, device=dev)
+        rc = self._lib.genztok_synth_device(self._h, 0, int(seed), int(doc0), int(n), int(side), int(lo), int(hi), thr, off.data_ptr(), data.data_ptr(), None, st)
+        if rc:
+            self._err(rc, "genztok_synth_device")
+        return data, off, nb
+
+    def digest_device(self, planes, row0, acc):
+        """acc (1-element int64 CUDA tensor) += order-independent digest of the [n, W] planes whose first row is global row `row0`."""
+        ids = planes["input_ids"]
+        n, W = ids.shape
+        tt = planes.get("token_type_ids")
+        rc = self._lib.genztok_digest_device(self._h, 0, ids.data_ptr(), planes["attention_mask"].data_ptr(), tt.data_ptr() if tt is not None else None,
+                                             int(n), int(W), int(row0), acc.data_ptr(), self._torch_stream(ids.device))
+        if rc:
+            self._err(rc, "genztok_digest_device")
+
+    def check_errors(self, device=None):
+        """Raises if the device pipeline counted an inconsistency (the asynchronous device path cannot report them itself)."""
+        import torch
+        n = C.c_int64()
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        rc = self._lib.genztok_check_errors(self._h, 0, self._torch_stream(dev), C.byref(n))
+        if rc:
+            self._err(rc, "genztok_check_errors")
+        return int(n.value)
+
     # ---- engine introspection ----------------------------------------------------------------------------
     def launch_count(self):
         return int(self._lib.genztok_launch_count(self._h))

@@ -189,6 +189,28 @@ int64_t genztok_profile_report(genztok_t *h, char *buf, int64_t cap, int reset);
  * kernel, 0 = auto), "wide_rows", "grid_mult".  Unknown names are an error. */
 int genztok_set_option(genztok_t *h, const char *name, int64_t value);
 
+/* Error counter of the asynchronous device path (genztok_encode_device / genztok_decode_device do not synchronise, so they
+ * cannot report what the kernels find: offsets outside the stated text, exhausted work lists).  Synchronises `stream`;
+ * *n_errors = inconsistencies counted since the handle was created; returns GENZTOK_E_CUDA when it is not zero. */
+int genztok_check_errors(genztok_t *h, int dev, void *stream, int64_t *n_errors);
+
+/* ---- measurement plumbing (not part of the reference's surface; used by bench.py and the tests) ------------------- */
+/* The synthetic workload of SURVEY.md 8 d2 produced on the device: the counter-based generator that
+ * genz_tokenize_b200/workload.py::generate_hashed defines (same bytes).  genztok_synth_init uploads the word list
+ * (packed words, start / length per word, 32-bit CDF of their counts) and the glue pieces of the noise words.
+ * genztok_synth_device, step 1 (d_bytes == NULL): byte offsets of documents [doc0, doc0 + n) of `side` into d_off[n+1],
+ * total in *total_bytes (synchronises); step 2: the bytes. */
+int genztok_synth_init(genztok_t *h, int dev, const uint8_t *wblob, int64_t wblob_len, const uint32_t *wstart,
+                       const uint32_t *wlen, const uint32_t *cdf32, int64_t nw, const uint8_t *eblob, int64_t eblob_len,
+                       const uint32_t *estart, const uint32_t *elen, int64_t ne);
+int genztok_synth_device(genztok_t *h, int dev, uint64_t seed, int64_t doc0, int64_t n, int side, int lo, int hi,
+                         uint32_t noise_thr, int64_t *d_off, uint8_t *d_bytes, int64_t *total_bytes, void *stream);
+/* Order-independent digest of fixed-layout planes on the device: *d_acc += sum over rows r and 32-bit words i of
+ * mix64((mix64((row0 + r) * GOLD) + (plane << 32 | i) * GOLD) ^ word), planes 0 = input_ids, 1 = attention_mask,
+ * 2 = token_type_ids (NULL: skipped).  Equal for any sharding / chunking of the same batch. */
+int genztok_digest_device(genztok_t *h, int dev, const int32_t *d_ids, const uint8_t *d_mask, const int8_t *d_tt,
+                          int64_t n, int32_t width, int64_t row0, uint64_t *d_acc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

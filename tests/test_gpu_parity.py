@@ -105,7 +105,7 @@ def test_bpe_strings(tok, golden):
 
 
 def test_sequence_id_state_machine(tok, golden):
-    for ids, raw, tt in golden["seqid"][::7]:
+    for ids, raw, tt in golden["seqid"]:           # all 5,460 sequences of the reference
         assert tok.get_sequence_id(ids) == raw, ids
         if tt == "ValueError":
             with pytest.raises(ValueError):
@@ -612,3 +612,102 @@ def test_one_handle_many_devices(oracle):
     assert multi.decode_batch(fix[:3]) == oracle.decode_batch(fix[:3].reshape(-1), np.arange(0, 3 * 64 + 1, 64, dtype=np.int64))
     few = multi.encode_batch((t[0][:t[1][3]], t[1][:4]), max_len=16)       # fewer rows than 2 x devices: one device does it all
     assert np.array_equal(few["input_ids"].reshape(-1), oracle.encode_batch((t[0][:t[1][3]], t[1][:4]), None, max_len=16)["ids"])
+
+
+# ---- round 2: the bench workload (BASELINE configs[2]) -- generator, digest, a full chunk against the oracle, the reference itself ----
+def _device_planes(tok, ta, tb, W, dev):
+    import torch
+    up = lambda a: torch.from_numpy(np.concatenate([a, np.zeros((-len(a)) % 16 + 32, dtype=np.uint8)])).to(dev)
+    out = tok.encode_device(up(ta[0]), torch.from_numpy(ta[1]).to(dev), up(tb[0]), torch.from_numpy(tb[1]).to(dev), max_len=W,
+                            text_bytes=len(ta[0]), pair_bytes=len(tb[0]))
+    torch.cuda.synchronize()
+    assert tok.check_errors(dev) == 0
+    return out
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.03])
+def test_synth_device_matches_host(tok, noise):
+    """csrc/synth.cuh produces the bytes workload.generate_hashed defines, for any document range and both sides."""
+    import torch
+    from genz_tokenize_b200 import workload
+    dev = torch.device("cuda:0")
+    for doc0, n, side in ((0, 5000, 0), (99_999_000, 3000, 1), (123_456_789, 1, 0)):
+        hb, ho = workload.generate_hashed(1234, doc0, n, side, 3, 13, noise)
+        db, do, nb = tok.synth_device(1234, doc0, n, side, 3, 13, noise, device=dev)
+        assert nb == len(hb)
+        assert np.array_equal(do.cpu().numpy(), ho)
+        assert np.array_equal(db[:nb].cpu().numpy(), hb)
+
+
+def test_plane_digest_device_matches_host_and_is_chunking_independent(tok):
+    import torch
+    from genz_tokenize_b200 import workload
+    dev = torch.device("cuda:0")
+    n, W = 6000, 64
+    ta, tb = workload.generate_hashed(7, 500, n, 0, 3, 13, 0.02), workload.generate_hashed(7, 500, n, 1, 3, 13, 0.02)
+    out = _device_planes(tok, ta, tb, W, dev)
+    want = workload.plane_digest(out["input_ids"].cpu().numpy(), out["attention_mask"].cpu().numpy(), out["token_type_ids"].cpu().numpy(), row0=500)
+    acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    tok.digest_device(out, 500, acc)
+    assert (int(acc.item()) & 0xFFFFFFFFFFFFFFFF) == want
+    acc2 = torch.zeros(1, dtype=torch.int64, device=dev)       # the same rows in three pieces, out of order
+    for lo, hi in ((4000, 6000), (0, 1500), (1500, 4000)):
+        tok.digest_device({k: v[lo:hi] for k, v in out.items() if v.dim() == 2}, 500 + lo, acc2)
+    assert int(acc2.item()) == int(acc.item())
+    out["input_ids"][1234, 3] += 1                               # ... and it sees a single changed id
+    acc3 = torch.zeros(1, dtype=torch.int64, device=dev)
+    tok.digest_device(out, 500, acc3)
+    assert int(acc3.item()) != int(acc.item())
+
+
+@pytest.mark.parametrize("doc0", [0, 37_500_000 + 7 * (1 << 20)])
+def test_config3_full_chunk_vs_oracle(oracle, doc0):
+    """A whole 1,048,576-pair chunk of the bench workload (the first one, and one from the middle of another shard) at max_len 256,
+    three planes, device-resident: every row against the oracle."""
+    import torch
+    from genz_tokenize_b200 import Tokenize, workload
+    from oracle.oracle import Oracle
+    dev = torch.device("cuda:0")
+    tok = Tokenize(devices=[0])
+    tok.set_option("max_chunk_bytes", 1 << 27)
+    n, W = 1 << 20, 256
+    da, oa, na = tok.synth_device(1234, doc0, n, 0, 3, 13, 0.0, device=dev)
+    db, ob, nb = tok.synth_device(1234, doc0, n, 1, 3, 13, 0.0, device=dev)
+    out = tok.encode_device(da, oa, db, ob, max_len=W, text_bytes=na, pair_bytes=nb)
+    torch.cuda.synchronize()
+    assert tok.check_errors(dev) == 0
+    ha, hb = (da[:na].cpu().numpy(), oa.cpu().numpy()), (db[:nb].cpu().numpy(), ob.cpu().numpy())
+    ref = oracle.encode_batch(ha, hb, max_len=W, threads=max(Oracle.max_threads(), os.cpu_count() or 1))
+    assert np.array_equal(out["input_ids"].cpu().numpy().reshape(-1), ref["ids"])
+    assert np.array_equal(out["attention_mask"].cpu().numpy().reshape(-1), ref["mask"])
+    assert np.array_equal(out["row_status"].cpu().numpy(), ref["status"])
+    tt = out["token_type_ids"].cpu().numpy()
+    assert (np.diff(ref["tt_off"]) == W).all()
+    assert np.array_equal(tt.reshape(-1).astype(np.int32), ref["tt"])
+    assert np.array_equal(out["seq_len"].cpu().numpy(), np.diff(ref["seq_off"]))
+    assert np.array_equal(out["row_len"].cpu().numpy().astype(np.int64), ref["mask"].reshape(n, W).sum(axis=1))
+
+
+def test_cuda_path_against_the_reference_itself(tok):
+    """When oracle/_ref travelled to this box (oracle/make_ref.py), compare the CUDA path with the UNMODIFIED Python reference
+    directly -- no oracle in between -- on noisy pairs of the bench workload, encode and decode."""
+    from oracle import ref_pool
+    if not ref_pool.available():
+        pytest.skip("oracle/_ref is not on this box")
+    from genz_tokenize_b200 import workload
+    n, W = 3000, 48
+    ta, tb = workload.generate_hashed(99, 10, n, 0, 3, 13, 0.05), workload.generate_hashed(99, 10, n, 1, 3, 13, 0.05)
+    sa, sb = workload.unpack(*ta), workload.unpack(*tb)
+    rows = ref_pool.encode_rows_single(sa, sb, W)
+    be = tok.encode_batch(ta, tb, max_len=W)
+    for i, r in enumerate(rows):
+        if r is None:
+            assert be["row_status"][i] == 1, i
+            continue
+        assert be["row_status"][i] == 0, i
+        got = tok._row_to_dict(be, i)
+        assert got == r, (i, sa[i], sb[i])
+    texts = tok.decode_batch(be["input_ids"][:500])
+    ref_tok = ref_pool._tok
+    for i in range(500):
+        assert texts[i] == ref_tok.decode(be["input_ids"][i].tolist()), i
