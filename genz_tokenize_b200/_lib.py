@@ -9,7 +9,7 @@ SO_PATH = os.environ.get("GENZTOK_LIB") or os.path.join(_HERE, "libgenztok.so") 
 
 MAX_LEN_NONE = -(2 ** 31)
 WANT_TOKEN_TYPE, WANT_SEQUENCE_ID, WANT_SPANS = 1, 2, 4
-NONE, EOS_MARK = -1, -3
+NONE, EOS_MARK, PAD_MARK = -1, -3, -4
 
 E_INVALID, E_IO, E_UTF8, E_CUDA, E_NOMEM, E_NODEVICE, E_LIMIT = -1, -2, -3, -4, -5, -6, -7
 

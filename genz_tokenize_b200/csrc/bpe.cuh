@@ -137,8 +137,11 @@ __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
         uint32_t n = bpe_symbols(T, key, len, S, lane);
         n = bpe_rounds(T, S, n, lane);
         uint32_t val;
-        if (n == 1) {
-            val = VAL_SINGLE | ((uint32_t)sym_to_id(T, S[0], true) & VAL_PAYLOAD);
+        // VAL_SINGLE promises "one token that is none of <s>, </s>, <pad>": a word that IS one of those ids (the text "</s>")
+        // is stored as a list of one, so that the row kernels meet it on their general path and never test ids in the common one
+        const int32_t id1 = n == 1 ? sym_to_id(T, S[0], true) : -1;
+        if (n == 1 && id1 != T.bos && id1 != T.eos && id1 != T.pad) {
+            val = VAL_SINGLE | ((uint32_t)id1 & VAL_PAYLOAD);
         } else {
             uint32_t off = scratch_off;
             if (!big) {

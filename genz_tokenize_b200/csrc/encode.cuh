@@ -77,6 +77,7 @@ struct RowArgs {
     uint32_t* redo_list;       // rows with cache misses (filled in pass 1)
     uint32_t* fix_list;        // rows whose token types need the generic kernel
     int8_t eos_i8;
+    int8_t pad_i8;             // what __padding appends to token_type_ids: the pad id (tokenize.py:143 via :257), GENZTOK_PAD_MARK when it does not fit
     // return_offset=True (tokenize.py:105-117,225-234): words per side (COUNT writes), span table (RAGGED writes)
     int32_t* nwA; int32_t* nwB;
     const int64_t* span_off;   // [n_rows+1] first span entry of each row
@@ -314,8 +315,9 @@ __device__ __noinline__ bool long_key_equal(const uint8_t* kp, const uint8_t* wp
     return diff == 0;
 }
 
-// Find the word in the cache or insert it (BPE pending).  Returns the slot's value word (VAL_*).
-// With insert_ok == false (second passes) an absent word is reported as VAL_PENDING and nothing is written.
+// Find the word in the cache or insert it (BPE pending).  Returns the slot's value word (VAL_*); for a word whose BPE has
+// not run yet that is VAL_PENDING | index of its slot, so that a later kernel can fetch the value without looking the word
+// up again.  With insert_ok == false (second passes) an absent word is reported as VAL_PENDING and nothing is written.
 __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, const uint8_t* wptr, uint32_t len, uint64_t k0, uint64_t k1,
                                                          uint64_t k2, uint32_t h, bool insert_ok) {
     uint32_t idx = h & C.mask;
@@ -330,7 +332,7 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
             bool eq;
             if (len <= KEY_INLINE) eq = (s0 == k0) & (s1 == k1) & (s2 == k2);
             else eq = s1 == k1 && long_key_equal(C.key_arena + s0, wptr, len);
-            if (eq) return a.y;
+            if (eq) return (a.y & VAL_KIND) == VAL_PENDING ? (VAL_PENDING | idx) : a.y;
         } else if (a.x == SLOT_EMPTY || a.x == SLOT_LOCKED) {
             if (!fresh) { fresh = true; continue; }          // L1 may be stale: look again in L2
             if (a.x == SLOT_LOCKED) continue;                // another thread is writing this slot
@@ -351,7 +353,7 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
             const uint64_t pi = atomicAdd(&C.ctr[C_PENDING], 1ULL);
             if (pi < C.pending_cap) C.pending[pi] = idx;
             else atomicAdd(&C.ctr[C_ERR], 1ULL);
-            return VAL_PENDING;
+            return VAL_PENDING | idx;
         }
         idx = (idx + 1) & C.mask;
         fresh = false;
@@ -418,10 +420,10 @@ __device__ __forceinline__ int32_t seq_value(const SeqDesc& d, int32_t i) {
     return v;
 }
 // token_type_ids / sequence_id bytes for positions i0..i0+3 of a fixed-width row
-__device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t W, int8_t eos_i8, uint32_t* ttw, uint32_t* sqw) {
+__device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t W, int8_t eos_i8, int8_t pad_i8, uint32_t* ttw, uint32_t* sqw) {
     const int32_t hi = i0 + 3;
     auto in4 = [&](int32_t v) { return v >= i0 && v <= hi; };
-    if (i0 >= d.m) { *ttw = 0; *sqw = 0xFEFEFEFEu; return; }
+    if (i0 >= d.m) { *ttw = 0x01010101u * (uint32_t)(uint8_t)pad_i8; *sqw = 0xFEFEFEFEu; return; }
     if (hi < d.m && !(in4(0) | in4(d.m - 1) | in4(d.f1) | in4(d.f2) | in4(d.r1) | in4(d.r2) | in4(d.p1))) {
         const uint32_t v = i0 < d.p1 ? 0u : 0x01010101u;
         *ttw = v; *sqw = v;
@@ -431,7 +433,7 @@ __device__ __forceinline__ void seq_words4(const SeqDesc& d, int32_t i0, int32_t
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int32_t i = i0 + k;
-        const int32_t sv = i < d.m ? seq_value(d, i) : 0;
+        const int32_t sv = i < d.m ? seq_value(d, i) : (int32_t)pad_i8;
         const int32_t tv = (d.m == W && i == W - 1) ? (int32_t)eos_i8 : sv;
         t |= ((uint32_t)tv & 0xFFu) << (8 * k);
         s |= ((uint32_t)(i < d.m ? sv : -2) & 0xFFu) << (8 * k);
@@ -594,7 +596,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                 if (MODE == MODE_FIXED) { dsts = rowbufs + (size_t)doc * Wp; lim = cap; }
                 else { dstg = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }
                 uint32_t fl = 0;
-                if (nt == 1) {
+                if ((val & VAL_KIND) == VAL_SINGLE) {                     // (a list of one token is a word that is itself a special id: bpe.cuh)
                     const int32_t t = (int32_t)(val & VAL_PAYLOAD);
                     if (t <= spec_max) { if (t == T.eos || t == T.bos) fl |= F_SPECIAL; if (t == T.pad) fl |= F_PADTOK; }
                     if (q < lim) { if (MODE == MODE_FIXED) dsts[q] = (TokT)t; else dstg[q] = t; }
@@ -784,7 +786,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                     reinterpret_cast<uint32_t*>(sm_mask)[d * qpr + q] = mk;
                     if (tma_tt) {
                         uint32_t ttw = 0, sqw;
-                        if (!(em & EM_SKIP)) seq_words4(ts->dsd[d], q * 4, W, A.eos_i8, &ttw, &sqw);
+                        if (!(em & EM_SKIP)) seq_words4(ts->dsd[d], q * 4, W, A.eos_i8, A.pad_i8, &ttw, &sqw);
                         reinterpret_cast<uint32_t*>(sm_tt)[d * qpr + q] = ttw;
                     }
                 }
@@ -853,7 +855,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                     if (A.mask) st_cs32(A.mask + g, mk);
                     if (A.has_pair && (A.tt || A.seq)) {
                         uint32_t ttw, sqw;
-                        seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                        seq_words4(ts->dsd[d], i0, W, A.eos_i8, A.pad_i8, &ttw, &sqw);
                         if (A.tt) st_cs32(A.tt + g, ttw);
                         if (A.seq) st_cs32(A.seq + g, sqw);
                     }
@@ -876,8 +878,8 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                         st_cs128(gi, pad4);
                         if (gm) st_cs32(gm + (size_t)d * W, 0u);
                         if (pairs_planes) {
-                            uint32_t ttw = 0u, sqw = 0xFEFEFEFEu;
-                            if ((long_rows >> d) & 1u) seq_words4(ts->dsd[d], i0, W, A.eos_i8, &ttw, &sqw);
+                            uint32_t ttw = 0x01010101u * (uint32_t)(uint8_t)A.pad_i8, sqw = 0xFEFEFEFEu;
+                            if ((long_rows >> d) & 1u) seq_words4(ts->dsd[d], i0, W, A.eos_i8, A.pad_i8, &ttw, &sqw);
                             const size_t g = grow + (size_t)d * W + i0;
                             if (A.tt) st_cs32(A.tt + g, ttw);
                             if (A.seq) st_cs32(A.seq + g, sqw);
@@ -900,7 +902,7 @@ __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowAr
                     if (A.mask) A.mask[dr * W + i] = (uint8_t)(t != T.pad);
                     if (A.has_pair) {
                         const SeqDesc& sd = ts->dsd[d];
-                        const int32_t sv = i < sd.m ? seq_value(sd, i) : 0;
+                        const int32_t sv = i < sd.m ? seq_value(sd, i) : (int32_t)A.pad_i8;
                         const int32_t tv = (sd.m == W && i == W - 1) ? (int32_t)A.eos_i8 : sv;
                         if (A.tt) A.tt[dr * W + i] = (int8_t)tv;
                         if (A.seq) A.seq[dr * W + i] = (int8_t)(i < sd.m ? sv : -2);

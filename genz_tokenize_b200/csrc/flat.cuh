@@ -9,13 +9,15 @@
 //                       bytes (tokenize.py:106  \S+\n?), the block compacts its word starts, then looks the words up in
 //                       the word cache one word per thread (tokenize.py:108-121; misses are inserted for k_bpe_pending)
 //                       and stores the cache value of every word at  block * 8192 + (index of the word in the block)
-//   k_flat_fix          after k_bpe_pending: the values of the words that were pending
+//                       (a word whose BPE is pending is stored as its slot index: k_flat_rows fetches the value after k_bpe_pending)
 //   k_flat_rows         a warp owns D rows: word ranges from the start bitmap (rank of the document offsets), framing,
 //                       truncation, padding, mask, token types (tokenize.py:126-182,222-258) staged in final form and
 //                       written by the TMA unit (TmaPlanes); rows it cannot finish go to the generic second pass
 //
 // Replaces the same reference lines as encode.cuh; outputs are bit-identical to the fused kernel's.
 #pragma once
+#include <type_traits>
+
 #include "encode.cuh"
 
 namespace gzt {
@@ -33,11 +35,7 @@ struct FlatSide {
     uint32_t* st;             // [nB*30 + 2] word-start bits per 32-byte granule
     uint16_t* tpref;          // [nB*30 + 2] words of the chunk before the granule
     uint32_t* cnt;            // [nB]        words per chunk
-    uint32_t* wtok;           // [nB*1024]   cache value (VAL_*) per word
-    uint32_t* fixa;           // pending words: index into wtok ...
-    uint32_t* fixp;           // ... and position (relative to P0)
-    uint32_t fix_cap;
-    int ctr_fix;              // counter index in WordCache::ctr
+    uint32_t* wtok;           // [nB*1024]   cache value (VAL_*) per word; VAL_PENDING | slot index while the word's BPE has not run
     uint32_t nB;              // chunks of FC_BYTES that cover the text (from the caller's byte count)
 };
 // end of the text relative to P0, never beyond what the work arrays cover (a caller that under-reports the byte
@@ -90,6 +88,12 @@ __device__ __noinline__ uint32_t lookup_len(const WordCache& C, const uint8_t* w
     return cache_find_or_insert(C, wptr_base + q, len, k0, k1, k2, h, insert_ok != 0);
 }
 
+// Everything the fast path of k_flat_words does not take: words longer than 16 bytes, words whose end lies beyond the bits the
+// warp holds (len 0: measured bytewise).  Out of line: the kernel is short of registers.
+__device__ __noinline__ uint32_t flat_lookup_general(const WordCache& C, const uint8_t* tb, const uint32_t* dsb, uint32_t q, uint32_t len, uint32_t hi, int insert_ok) {
+    return lookup_len(C, tb, q, len ? len : flat_word_len(tb, dsb, q, hi), insert_ok);
+}
+
 // Terminator and newline bits of the granule behind a block, so that the block's last words end inside known bits:
 // only its plain-ASCII case (a high byte there leaves the bits unknown and such a word is measured bytewise).
 __device__ __noinline__ void flat_lookahead(const uint8_t* tb, const uint32_t* dsb, uint32_t qn, uint32_t hi, uint32_t* term, uint32_t* nl) {
@@ -135,6 +139,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 }
 // The slots of the frequent words are read again and again while hundreds of MB of planes stream through L2: the probes ask
 // L2 to evict those lines last, so that a batch of probes does not wait for the one that had to go to DRAM.
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -143,6 +152,24 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 __device__ __forceinline__ uint4 ld_keep128(const uint4* p, uint64_t policy) {
     uint4 v;
     asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+// streaming reads (text, offsets: read once) must not push the word arrays out of L2 either
+__device__ __forceinline__ uint4 ld_stream128(const void* p, uint64_t policy) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_keep32(void* p, uint32_t v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_keep16(void* p, uint16_t v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint2 ld_keep64(const void* p, uint64_t policy) {
+    uint2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(policy));
     return v;
 }
 __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t smem_addr, int32_t c0, int32_t c1, uint64_t policy) {
@@ -159,12 +186,15 @@ struct PadJob {
     int32_t W, D, KR, PB;
     int32_t want_tt;
     int32_t pad_id;
+    int32_t l2_policy;   // bit 0: the text is read with the L2 evict-first policy; bit 1: the word arrays are stored with evict-last (experiments)
+    uint32_t ratio;      // ceil(n_tiles * 2^20 / chunks of the launch): chunk c takes tiles [c * ratio >> 20, (c + 1) * ratio >> 20), clipped to n_tiles
 };
 
 // tiles [c * n_tiles / n_chunks, (c + 1) * n_tiles / n_chunks) of the pad columns; one thread.  Out of line: k_flat_words
 // is short of registers.
 __device__ __noinline__ void flat_pad_tiles(const PadJob& J, const TmaPlanes& M, uint32_t c, uint32_t n_chunks, uint32_t pad_s, uint32_t zeros_s, uint64_t l2_first) {
-    const uint32_t t0 = (uint32_t)((uint64_t)c * (uint32_t)J.n_tiles / n_chunks), t1 = (uint32_t)(((uint64_t)c + 1) * (uint32_t)J.n_tiles / n_chunks);
+    (void)n_chunks;
+    const uint32_t t0 = min((uint32_t)J.n_tiles, (uint32_t)(((uint64_t)c * J.ratio) >> 20)), t1 = min((uint32_t)J.n_tiles, (uint32_t)((((uint64_t)c + 1) * J.ratio) >> 20));
     for (uint32_t t = t0; t < t1; t++) {
         const int32_t r = (int32_t)((t + (uint32_t)J.tile0) * (uint32_t)J.D);
         for (int32_t c0 = J.KR; c0 < J.W; c0 += J.PB) {
@@ -185,15 +215,35 @@ struct FlatWarpSmem {
     uint8_t text[1024 + 16];       // the 32 classified granules and 16 bytes more (key gathers)
     uint16_t wl[1024];             // words: position in the classified window | length << 10
 };
+// Both sides of a pair batch in one launch: blocks [0, blocks_a) walk side 0, the others side 1.
+struct FlatWordsArgs {
+    FlatSide side[2];
+    PadJob job[2];
+    uint32_t blocks_a;
+    int32_t insert_ok;
+};
 template <int MINB, int ILP>
-__global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, FlatSide S, int insert_ok, PadJob J, const __grid_constant__ TmaPlanes M) {
+__global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, const __grid_constant__ FlatWordsArgs P, const __grid_constant__ TmaPlanes M) {
     pdl_wait(); pdl_trigger();
+    const int which = blockIdx.x >= P.blocks_a ? 1 : 0;
+    const FlatSide& S = P.side[which];
+    const PadJob& J = P.job[which];
+    const int insert_ok = P.insert_ok;
+    const uint32_t block_id = blockIdx.x - (which ? P.blocks_a : 0u), n_blocks = which ? gridDim.x - P.blocks_a : P.blocks_a;
     __shared__ __align__(16) FlatWarpSmem s_warp[FW_WARPS];
+    __shared__ uint4 s_keymask[17];                                          // byte masks of a 16-byte key by length
     extern __shared__ __align__(1024) uint8_t pad_smem[];                   // J.on: [D x PB] pad ids, [D x PB] zero bytes
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if (tid < 17) {
+        auto m32 = [&](int i) -> uint32_t { const int nb = min(max(tid - 4 * i, 0), 4); return nb ? (0xFFFFFFFFu >> (8 * (4 - nb))) : 0u; };
+        s_keymask[tid] = make_uint4(m32(0), m32(1), m32(2), m32(3));
+    }
+    __syncthreads();
     FlatWarpSmem& sm = s_warp[wib];
     uint32_t pad_s = 0, zeros_s = 0; uint64_t l2_first = 0;
     const uint64_t l2_last = l2_policy_evict_last();
+    const uint64_t l2_stream = (J.l2_policy & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t l2_keep = (J.l2_policy & 2) ? l2_last : l2_policy_evict_normal();
     if (J.on) {
         const uint4 pad4 = make_uint4((uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id, (uint32_t)J.pad_id);
         uint4* cp = reinterpret_cast<uint4*>(pad_smem);
@@ -209,7 +259,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
     const int64_t P0 = o0 & ~(int64_t)15;
     const uint8_t* __restrict__ tb = S.bytes + P0;
     const uint32_t lo = (uint32_t)(o0 - P0), hi = flat_hi(S, P0);   // the text is [lo, hi)
-    const uint32_t n_warps = gridDim.x * (uint32_t)FW_WARPS;
+    const uint32_t n_warps = n_blocks * (uint32_t)FW_WARPS;
     // granule of this lane in chunk c is 30c - 1 + lane; its bytes start at q0 (may be "negative" for chunk 0, lane 0)
     const uint4 sp = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
     uint4 nv0 = sp, nv1 = sp, nv2 = sp; uint32_t ndsb = 0;
@@ -219,13 +269,13 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
         const int64_t gq = ((int64_t)c * FC_OWN - 1 + lane) * 32;
         if (gq >= 0) {
             const uint32_t q0 = (uint32_t)gq;
-            if (q0 < hi) nv0 = ldg128(tb + q0);
-            if (q0 + 16 < hi) nv1 = ldg128(tb + q0 + 16);
-            if (lane == 31 && q0 + 32 < hi) nv2 = ldg128(tb + q0 + 32);
+            if (q0 < hi) nv0 = ld_stream128(tb + q0, l2_stream);
+            if (q0 + 16 < hi) nv1 = ld_stream128(tb + q0 + 16, l2_stream);
+            if (lane == 31 && q0 + 32 < hi) nv2 = ld_stream128(tb + q0 + 32, l2_stream);
             ndsb = S.dsb[q0 >> 5];
         }
     };
-    uint32_t c = blockIdx.x * (uint32_t)FW_WARPS + wib;
+    uint32_t c = block_id * (uint32_t)FW_WARPS + wib;
     load_chunk(c);
     for (; c < S.nB; c += n_warps) {
         const uint4 v0 = nv0, v1 = nv1, v2 = nv2;
@@ -314,8 +364,9 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
         const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
         const uint32_t pref = incl - cnt;
-        if (own) { S.st[q0 >> 5] = st; S.tpref[q0 >> 5] = (uint16_t)pref; }
-        if (lane == 0) S.cnt[c] = total;
+        // (what k_flat_rows reads right after this kernel: kept in L2 while the text and the planes stream through)
+        if (own) { st_keep32(&S.st[q0 >> 5], st, l2_keep); st_keep16(&S.tpref[q0 >> 5], (uint16_t)pref, l2_keep); }
+        if (lane == 0) st_keep32(&S.cnt[c], total, l2_keep);
         // my words: position and length (terminator bits of my granule and the next one; the newline a word takes along
         // is the terminator itself).  Length 0: the end is further away, the word is measured bytewise.
         {
@@ -336,81 +387,38 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
             }
         }
         __syncwarp();
-        // one word per lane: its key from the staged text (aligned 16-byte pieces + funnel shifts), one probe of the word's
-        // home slot -- the second half of the slot only for words longer than 8 bytes
+        // one word per lane.  Words of up to 16 bytes (99.4 % of the occurrences of the vocabulary's text): the key is the five
+        // aligned 32-bit words of the staged text around it, funnel-shifted to its start and cut to its length by a mask
+        // from a table; the hash of device_common.cuh::hash_key24 restricted to those four key words; one probe of the word's
+        // home slot (16 bytes, 8 more for keys longer than 8 bytes).  Everything else is out of line.
         uint32_t* const wtok = S.wtok + ((size_t)c << FC_SHIFT);
-        // (two words per lane and step: both probes are in flight before either is examined)
-        auto prep = [&](uint32_t i, uint32_t& p, uint32_t& len, uint64_t& k0, uint64_t& k1, uint64_t& k2, uint32_t& h, uint4& a, uint4& b) {
-            // returns true when the word takes the fast path (key in k0..k2, slot halves being loaded into a / b)
-            a = make_uint4(0u, 0u, 0u, 0u); b = a; p = 0; len = 0; k0 = k1 = k2 = 0; h = 0;
-            if (i >= total) return false;
+        for (uint32_t i = lane; i < total; i += 32) {
             const uint32_t e = sm.wl[i];
-            p = e & 1023u; len = e >> 10;
-            if (len == 0 || len > KEY_INLINE) return false;
-            const uint32_t a16 = p & ~15u;
-            const int s16 = (int)(p & 15u);
-            const uint4 x0 = *reinterpret_cast<const uint4*>(text + a16);
-            const uint4 x1 = *reinterpret_cast<const uint4*>(text + a16 + 16);
-            uint2 x2 = make_uint2(0u, 0u);
-            if (s16 + (int)len > 32) x2 = *reinterpret_cast<const uint2*>(text + a16 + 32);
-            key_from_pieces40_nomask(x0, x1, x2, s16, &k0, &k1, &k2);
-            key_mask24(len, &k0, &k1, &k2);
-            h = hash_key24(k0, k1, k2, len);
-            const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
-            a = ld_keep128(slot, l2_last);
-            if (len > 8) b = ld_keep128(slot + 1, l2_last);          // (equal lengths <= 8: the rest of both keys is zero)
-            return true;
-        };
-        auto done = [&](uint32_t i, bool fast, uint32_t p, uint32_t len, uint64_t k0, uint64_t k1, uint64_t k2, uint32_t h, const uint4& a, const uint4& b) {
-            if (i >= total) return;
+            const uint32_t p = e & 1023u, len = e >> 10;
             uint32_t val;
-            if (fast) {
-                const uint64_t s0 = ((uint64_t)a.w << 32) | a.z, s1 = ((uint64_t)b.y << 32) | b.x, s2 = ((uint64_t)b.w << 32) | b.z;
+            if (len - 1u < 16u) {
+                const uint32_t* tw = reinterpret_cast<const uint32_t*>(text + (p & ~3u));
+                const uint32_t w0 = tw[0], w1 = tw[1], w2 = tw[2], w3 = tw[3], w4 = tw[4];
+                const uint32_t sh = (p & 3u) * 8u;
+                const uint4 mk = s_keymask[len];
+                const uint32_t k0 = __funnelshift_r(w0, w1, sh) & mk.x, k1 = __funnelshift_r(w1, w2, sh) & mk.y;
+                const uint32_t k2 = __funnelshift_r(w2, w3, sh) & mk.z, k3 = __funnelshift_r(w3, w4, sh) & mk.w;
+                uint32_t h = len * 0x9E3779B1u + k0 * 0xcc9e2d51u + k1 * 0x1b873593u + k2 * 0x85ebca6bu + k3 * 0xc2b2ae35u;
+                h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+                const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
+                const uint4 a = ld_keep128(slot, l2_last);
+                uint2 b2 = make_uint2(0u, 0u);
+                if (len > 8u) b2 = ld_keep64(slot + 1, l2_last);           // (equal lengths <= 8: the rest of both keys is zero)
                 val = a.y;
-                if (!((a.x == len) & (s0 == k0) & (s1 == k1) & (s2 == k2))) val = cache_find_or_insert(C, tb + wq + p, len, k0, k1, k2, h, insert_ok != 0);
-            } else val = lookup_len(C, tb, wq + p, len ? len : flat_word_len(tb, S.dsb, wq + p, hi), insert_ok);
-            if ((val & VAL_KIND) == VAL_PENDING) {
-                const unsigned long long k = atomicAdd(&C.ctr[S.ctr_fix], 1ULL);
-                if (k < S.fix_cap) { S.fixa[k] = (c << FC_SHIFT) + i; S.fixp[k] = wq + p; }
-                else atomicAdd(&C.ctr[C_ERR], 1ULL);
-            }
-            wtok[i] = val;
-        };
-        if (ILP == 2) {
-            for (uint32_t base = 0; base < total; base += 64) {
-                const uint32_t i1 = base + lane, i2 = i1 + 32;
-                uint32_t p1, l1, h1, p2, l2, h2; uint64_t ka0, ka1, ka2, kb0, kb1, kb2; uint4 a1, b1, a2, b2;
-                const bool f1 = prep(i1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
-                const bool f2 = prep(i2, p2, l2, kb0, kb1, kb2, h2, a2, b2);
-                done(i1, f1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
-                done(i2, f2, p2, l2, kb0, kb1, kb2, h2, a2, b2);
-            }
-        } else {
-            for (uint32_t i = lane; i < total; i += 32) {
-                uint32_t p1, l1, h1; uint64_t ka0, ka1, ka2; uint4 a1, b1;
-                const bool f1 = prep(i, p1, l1, ka0, ka1, ka2, h1, a1, b1);
-                done(i, f1, p1, l1, ka0, ka1, ka2, h1, a1, b1);
-            }
+                if (!((a.x == len) & (a.z == k0) & (a.w == k1) & (b2.x == k2) & (b2.y == k3)))
+                    val = cache_find_or_insert(C, tb + wq + p, len, ((uint64_t)k1 << 32) | k0, ((uint64_t)k3 << 32) | k2, 0ULL, h, insert_ok != 0);
+                else if ((val & VAL_KIND) == VAL_PENDING) val = VAL_PENDING | (h & C.mask);          // its BPE has not run: hand on the slot
+            } else val = flat_lookup_general(C, tb, S.dsb, wq + p, len, hi, insert_ok);
+            st_keep32(&wtok[i], val, l2_keep);
         }
     }
     if (J.on && lane == 0) bulk_wait<0>();      // the constant buffer must outlive the tensor stores that read it
     __syncwarp();
-}
-
-// after k_bpe_pending: every pending word has its tokens now
-__global__ void k_flat_fix(WordCache C, FlatSide S) {
-    pdl_wait(); pdl_trigger();
-    const int64_t o0 = S.off[0];
-    const int64_t P0 = o0 & ~(int64_t)15;
-    const uint8_t* tb = S.bytes + P0;
-    const uint32_t hi = flat_hi(S, P0);
-    const unsigned long long n = min(C.ctr[S.ctr_fix], (unsigned long long)S.fix_cap);
-    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t q = S.fixp[k];
-        const uint32_t val = lookup_len(C, tb, q, flat_word_len(tb, S.dsb, q, hi), 0);
-        if ((val & VAL_KIND) == VAL_PENDING) atomicAdd(&C.ctr[C_ERR], 1ULL);
-        S.wtok[S.fixa[k]] = val;
-    }
 }
 
 // ---- rows ----------------------------------------------------------------------------------------------------
@@ -423,24 +431,29 @@ struct FlatRowsArgs {
     int8_t* tt;                    // non-null: token types wanted
     int32_t* row_len; int32_t* seq_len; uint8_t* status;
     uint32_t* redo_list; uint32_t* fix_list;
-    int8_t eos_i8;
+    int8_t eos_i8, pad_i8;
+    uint32_t pad_tile0;            // M.PB != 0: this kernel stores the pad columns of its tiles from this one on (the tiles before it are k_flat_words')
 };
 struct __align__(16) FlatTile {
-    uint32_t base[2][32];          // wtok index of the row's first word, per side
-    uint32_t avail[2][32];         // words of the row that lie in the block of the first one
-    uint32_t nw[2][32];            // words of the row
-    int32_t dnA[32], dL[32];       // tokens of side A, framed length
-    uint32_t dflag[32];
-    uint32_t demit[32];
-    SeqDesc dsd[32];
-    int32_t tlo[32];               // pairs, the usual row: token types are 1 exactly on [tlo, m) -- else -1 (closed form per quad)
+    // per row of the tile, in the form the column lanes need (all word indices are into a.wtok; side B's array follows side A's):
+    uint4 fa[32];                  // offA1, offA2, thA, nA1: column j in [1, nA1) holds word j - 1 of A, found at j + (j < thA ? offA1 : offA2)
+                                   //   (a row's words lie in at most two chunks' segments of wtok; thA = where the second one starts)
+    uint4 fb[32];                  // offB1, offB2, thB, e2: column j in [nA1 + 2, e2) holds a word of B, found at j + (j < thB ? offB1 : offB2)
+    uint4 fc[32];                  // framed length L, tlo (pairs, the usual row: token types are 1 exactly on [tlo, m); else -1), m, flags
+    uint32_t stage[32][32];        // columns 0..31 of the tile's rows in final form (the rebuild buffer of a row on the general path aliases it)
 };
+static const uint32_t FR_SLOW = 1u;    // the row takes the general path (whole warp, token scan)
+static const uint32_t FR_ERR = 2u;     // pairs: the reference raises ValueError for this row
 static const uint32_t FF_AGAIN = 8u;   // the row goes to the generic second pass
 
 __device__ __forceinline__ uint32_t flat_rank(const FlatSide& S, uint32_t q, uint32_t* blk) {
     const uint32_t gi = q >> 5;
     *blk = q / (uint32_t)FC_BYTES;
     return (uint32_t)S.tpref[gi] + __popc(S.st[gi] & ((1u << (q & 31)) - 1u));
+}
+// value of a word as k_flat_words stored it; a word that was pending then has its tokens by now (k_bpe_pending ran in between)
+__device__ __forceinline__ uint32_t flat_resolve(const WordCache& C, uint32_t val) {
+    return (val & VAL_KIND) == VAL_PENDING ? C.slots[val & VAL_PAYLOAD].val : val;
 }
 // index into wtok of word i of a row (first word at `base` in block base >> 13, `avail` words in that block)
 __device__ __forceinline__ uint32_t flat_word_index(const FlatSide& S, uint32_t base, uint32_t avail, uint32_t i) {
@@ -462,7 +475,7 @@ __device__ __forceinline__ int32_t flat_side_tokens(const DevTables& T, const Wo
         const uint32_t i = i0 + lane;
         uint32_t val = 0, nt = 0;
         if (i < nw) {
-            val = S.wtok[flat_word_index(S, base, avail, i)];
+            val = flat_resolve(C, S.wtok[flat_word_index(S, base, avail, i)]);
             nt = (val & VAL_KIND) == VAL_SINGLE ? 1u : ((val & VAL_KIND) == VAL_MULTI ? C.tok_arena[val & VAL_PAYLOAD] : 0u);
         }
         uint32_t sc = nt;
@@ -470,7 +483,7 @@ __device__ __forceinline__ int32_t flat_side_tokens(const DevTables& T, const Wo
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o); if (lane >= o) sc += t; }
         int32_t q = pos + (int32_t)(sc - nt);
         uint32_t fl = 0;
-        if (nt == 1) {
+        if ((val & VAL_KIND) == VAL_SINGLE) {
             const int32_t t = (int32_t)(val & VAL_PAYLOAD);
             if (t <= spec_max && (t == T.eos || t == T.bos || t == T.pad)) fl = FF_AGAIN;
             if (q < cap) row[q] = t;
@@ -488,46 +501,63 @@ __device__ __forceinline__ int32_t flat_side_tokens(const DevTables& T, const Wo
     return pos;
 }
 
-// Rows.  The staged ("real") columns 0..KR-1 of a row are computed four positions per lane and stored straight from
-// registers (16-byte streaming stores); the pad columns KR..W-1 -- most of the bytes -- are written by the TMA unit from
-// a block-wide constant buffer, two tensor stores per tile of D rows, with nothing to wait for.
+// Rows.  A warp owns a tile of 32 consecutive rows.
+//  1. One lane per row turns the row's document offsets into word ranges (ranks in the start bitmap), the framed length and,
+//     for pairs, the token-type description (tokenize.py:154-182 in closed form).
+//  2. The usual row -- every word one token, at most 32 tokens, usual token types -- is assembled a LANE PER COLUMN: column j is
+//     <s>, a word of A, </s>, </s>, a word of B, </s> or <pad> by position alone (tokenize.py:135,237-239,141-146), its value one
+//     coalesced load from the word arrays; the 32 x 32 ids go to shared memory.
+//  3. The planes are written a lane per 16 BYTES: the staged ids, the pad ids of the other staged columns, and mask / token
+//     types as closed forms of the row's lengths (tokenize.py:148-152,254-258) from a table of 16-byte runs of ones.
+//  4. A row that is not usual (a multi-token or pending-at-lookup word, more than 32 tokens, three chunks of text, unusual
+//     token types) is rebuilt by the whole warp through a token scan; a row that needs more than the KR staged columns, or holds
+//     a special id inside the text, goes to the generic second pass.
+// The pad columns KR..W-1 are constant boxes written by the TMA unit (by k_flat_words on the side, or here for the tiles from
+// pad_tile0 on).
 template <int MINB, bool PAIR>
 __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache C, FlatRowsArgs A, const __grid_constant__ TmaPlanes M) {
     pdl_wait(); pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint4 s_ones[17];                                         // n bytes of 0x01 followed by zeros, n = 0..16
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D, KR = M.KR, PB = M.PB;
     constexpr bool pair = PAIR;
     const bool want_tt = pair && A.tt;
     const uint32_t const_b = PB ? (uint32_t)tma_const_bytes(D, PB) : 0u;
-    const uint32_t per_warp = (uint32_t)r128(sizeof(FlatTile)) + (uint32_t)r128((size_t)KR * 4);
+    const uint32_t per_warp = (uint32_t)r128(sizeof(FlatTile));
     FlatTile* ts = reinterpret_cast<FlatTile*>(smem_raw + const_b + (size_t)wib * per_warp);
-    int32_t* const rebuild = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(ts) + r128(sizeof(FlatTile)));
+    int32_t* const rebuild = reinterpret_cast<int32_t*>(&ts->stage[0][0]);           // KR <= 256 ids
     const uint32_t const_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t zeros_s = const_s + (uint32_t)r128((size_t)D * PB * 4);
+    if (threadIdx.x < 17) {
+        auto m32 = [&](int i) -> uint32_t { const int nb = min(max((int)threadIdx.x - 4 * i, 0), 4); return nb ? (0x01010101u >> (8 * (4 - nb))) : 0u; };
+        s_ones[threadIdx.x] = make_uint4(m32(0), m32(1), m32(2), m32(3));
+    }
     if (PB) {
         const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
         uint4* cp = reinterpret_cast<uint4*>(smem_raw);
         const int n_pad = (int)(r128((size_t)D * PB * 4) >> 4), n_all = (int)(const_b >> 4);
         for (int i = threadIdx.x; i < n_all; i += blockDim.x) cp[i] = i < n_pad ? pad4 : make_uint4(0, 0, 0, 0);
         fence_proxy_async_smem();
-        __syncthreads();
     }
+    __syncthreads();
     const int64_t P0a = A.a.off[0] & ~(int64_t)15;
     const int64_t P0b = pair ? (A.b.off[0] & ~(int64_t)15) : 0;
+    const uint32_t* __restrict__ const wtok = A.a.wtok;
+    const uint32_t segB = pair ? (uint32_t)(A.b.wtok - A.a.wtok) : 0u;   // side B's word array follows side A's in one allocation
     const int32_t limit = W - 1;
     const int32_t cap = min(limit, KR);
-    const int32_t spec_max = max(T.pad, max(T.bos, T.eos));
-    const int32_t qpr = KR >> 2;                                       // quads per row in the real columns
+    const int32_t KQ = KR >> 2;                                          // 16-byte units of an ids row in the staged columns
     const uint32_t nw_clamp = (uint32_t)W + 8u;                          // more words than this cannot matter
     const uint32_t n_tiles = (uint32_t)((A.n_rows + D - 1) / D);
     const uint32_t n_warps = gridDim.x * (uint32_t)wpb;
+    const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
     uint32_t tok_total = 0;
     const uint64_t l2_first = l2_policy_evict_first();
     // Two loads head a tile's chain of dependent loads: the document offsets of my row, then the start bits / prefix of the
     // two granules they point into.  Both are issued ahead: the offsets two tiles ahead, the rank data one tile ahead.
     int64_t pre[2][2] = {{0, 0}, {0, 0}};
-    uint32_t nq[2][2] = {{0, 0}, {0, 0}}, ntp[2][2] = {{0, 0}, {0, 0}}, nst[2][2] = {{0, 0}, {0, 0}};
+    uint32_t nq[2][2] = {{0, 0}, {0, 0}}, ntp[2][2] = {{0, 0}, {0, 0}}, nst[2][2] = {{0, 0}, {0, 0}}, ncn[2] = {0, 0};
     auto prefetch_offsets = [&](uint32_t tile) {
         if (tile >= n_tiles) return;
         const int64_t r = (int64_t)tile * D + lane;
@@ -552,6 +582,8 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                     ntp[s][e] = S.tpref[q >> 5];
                     nst[s][e] = S.st[q >> 5];
                 }
+                // a row that runs over into the next chunk needs the word count of its first one
+                if (nq[s][0] / (uint32_t)FC_BYTES != nq[s][1] / (uint32_t)FC_BYTES) ncn[s] = S.cnt[nq[s][0] / (uint32_t)FC_BYTES];
             }
         }
     };
@@ -568,10 +600,11 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
         const uint32_t cq[2][2] = {{nq[0][0], nq[0][1]}, {nq[1][0], nq[1][1]}};
         const uint32_t ctp[2][2] = {{ntp[0][0], ntp[0][1]}, {ntp[1][0], ntp[1][1]}};
         const uint32_t cst[2][2] = {{nst[0][0], nst[0][1]}, {nst[1][0], nst[1][1]}};
+        const uint32_t ccn[2] = {ncn[0], ncn[1]};
         prefetch_ranks(tile + n_warps);
         prefetch_offsets(tile + 2 * n_warps);
         // ---- the pad columns of the tile: nothing to compute (rows that turn out longer are redone as a whole later)
-        if (PB && lane == 0) {
+        if (PB && tile >= A.pad_tile0 && lane == 0) {
             const int32_t r = (int32_t)r0;
             for (int32_t c0 = KR; c0 < W; c0 += PB) {
                 tma_store_2d_hint(&M.ids_pad, const_s, c0, r, l2_first);
@@ -580,11 +613,13 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
             }
             bulk_commit();
         }
-        // ---- 1. word ranges of my rows (one lane per row) from the ranks of the document offsets; framed length and
-        //         token types as if every word were one token (the usual case)
+        // ---- 1. my row (one lane per row): word ranges from the ranks of the document offsets; framed length and token
+        //         types as if every word were one token (the usual case)
+        uint32_t my_flags = 0;
         if (lane < nd) {
-            uint32_t nws[2] = {0u, 0u};
-            for (int s = 0; s < (pair ? 2 : 1); s++) {
+            uint32_t f[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};       // first word's index, words in its chunk, words, index of the next chunk's first word
+#pragma unroll
+            for (int s = 0; s < (PAIR ? 2 : 1); s++) {
                 const FlatSide& S = s ? A.b : A.a;
                 const uint32_t q0 = cq[s][0], q1 = cq[s][1];
                 const uint32_t b0 = q0 / (uint32_t)FC_BYTES, b1 = q1 / (uint32_t)FC_BYTES;
@@ -592,133 +627,167 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                 uint32_t nw, avail;
                 if (b0 == b1) { nw = rl1 - rl0; avail = nw; }
                 else {
-                    avail = S.cnt[b0] - rl0;
+                    avail = ccn[s] - rl0;
                     nw = avail + rl1;
-                    for (uint32_t b = b0 + 1; b < b1 && nw < nw_clamp; b++) nw += S.cnt[b];
+                    if (b1 > b0 + 1) {                                        // three or more chunks of text: the general path
+                        my_flags |= FR_SLOW;
+                        for (uint32_t b = b0 + 1; b < b1 && nw < nw_clamp; b++) nw += S.cnt[b];
+                    }
                 }
                 nw = min(nw, nw_clamp);
-                ts->base[s][lane] = (b0 << FC_SHIFT) + rl0;
-                ts->avail[s][lane] = avail;
-                ts->nw[s][lane] = nw;
-                nws[s] = nw;
+                f[s][0] = (b0 << FC_SHIFT) + rl0; f[s][1] = avail; f[s][2] = nw; f[s][3] = (b0 + 1u) << FC_SHIFT;
             }
-            const int32_t dL = (int32_t)(nws[0] + 2u + (pair ? nws[1] + 2u : 0u));
-            ts->dnA[lane] = (int32_t)nws[0];
-            ts->dL[lane] = dL;
-            ts->dflag[lane] = 0u;
+            const int32_t dL = (int32_t)(f[0][2] + 2u + (pair ? f[1][2] + 2u : 0u));
+            int32_t tlo = -1, m = 0;
             if (pair) {
-                const SeqDesc sd = seq_describe((int32_t)nws[0], dL, W);
-                ts->dsd[lane] = sd;
+                const SeqDesc sd = seq_describe((int32_t)f[0][2], dL, W);
                 // no residual None, the two None of the framing become 0 / 1 right behind A, no trailing eos id: 0..0 1..1 0..0
-                ts->tlo[lane] = (!sd.err && sd.r1 < 0 && sd.r2 < 0 && sd.f1 == sd.p1 && sd.f2 == sd.p1 + 1 && sd.m < W && sd.p1 > 0) ? sd.p1 + 1 : -1;
+                tlo = (!sd.err && sd.r1 < 0 && sd.r2 < 0 && sd.f1 == sd.p1 && sd.f2 == sd.p1 + 1 && sd.m < W && sd.p1 > 0) ? sd.p1 + 1 : -1;
+                m = sd.m;
+                if (sd.err) my_flags |= FR_ERR;
+                if (tlo < 0) my_flags |= FR_SLOW;
             }
+            if (dL > 32 || KR < 32) my_flags |= FR_SLOW;
+            const uint32_t nA1 = f[0][2] + 1u, bc0 = nA1 + 2u;
+            // the words of my row: asked for now, used in step 2 (they come from DRAM more often than from L2)
+            if (!(my_flags & FR_SLOW)) {
+                prefetch_l2(wtok + f[0][0]); prefetch_l2(wtok + f[0][0] + (f[0][1] ? f[0][1] - 1u : 0u));
+                if (pair) { prefetch_l2(wtok + segB + f[1][0]); prefetch_l2(wtok + segB + f[1][0] + (f[1][1] ? f[1][1] - 1u : 0u)); }
+            }
+            ts->fa[lane] = make_uint4(f[0][0] - 1u, f[0][3] - f[0][1] - 1u, f[0][1] + 1u, nA1);
+            ts->fb[lane] = make_uint4(segB + f[1][0] - bc0, segB + f[1][3] - f[1][1] - bc0, bc0 + f[1][1], bc0 + f[1][2]);
+            ts->fc[lane] = make_uint4((uint32_t)dL, (uint32_t)tlo, (uint32_t)m, my_flags);
         }
         __syncwarp();
-        // ---- 2. the real columns of every row, four lanes per row, four positions per lane and step: ids, mask, token types
-        for (int dg = 0; dg < D; dg += 8) {                              // (uniform trip count: the ballots below need every lane)
-            const int d = dg + (lane >> 2);
-            const bool live = d < nd;
-            const uint32_t nwA = live ? ts->nw[0][d] : 0u, baseA = ts->base[0][d], availA = ts->avail[0][d];
-            const uint32_t nwB = pair && live ? ts->nw[1][d] : 0u, baseB = pair ? ts->base[1][d] : 0u, availB = pair ? ts->avail[1][d] : 0u;
-            const int32_t L = live ? ts->dL[d] : 0;
-            const int32_t Lr = min(L, W);
-            const uint32_t b0 = nwA + 3u, e2 = nwA + nwB + 3u;          // pairs: first position of B, position of the closing </s>
-            const size_t grow = (size_t)(r0 + d) * (size_t)W;
-            bool odd = false, special = false;
-            const uint32_t a1 = nwA + 1u;                                  // position of the </s> behind A
-            const bool cut = L >= W;                                       // truncated: the last column is </s> (tokenize.py:145)
-            // the longest row of the group: behind it every quad of every row is padding (a warp-uniform test, no divergence)
-            const int32_t gmax = __reduce_max_sync(FULL_MASK, live ? Lr : 0);
-            const bool tt_plain = !(PAIR && want_tt) || __all_sync(FULL_MASK, !live || ts->tlo[d] >= 0);
-            for (int32_t q = lane & 3; q < qpr && live; q += 4) {
-                const int32_t j0 = q * 4;
-                if ((q & ~3) * 4 >= gmax && tt_plain) {
-                    st_cs128(A.ids + grow + j0, make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad));
-                    st_cs32(A.mask + grow + j0, 0u);
-                    if (PAIR && want_tt) st_cs32(A.tt + grow + j0, 0u);
-                    continue;
-                }
-                // the four words (if any) first: independent loads, one round trip
-                uint32_t val[4]; bool inA[4], inB[4];
+        uint32_t slow_rows = __ballot_sync(FULL_MASK, (my_flags & FR_SLOW) != 0);
+        // ---- 2. the usual rows, a lane per column: 32 ids per row into the staging area.  Eight rows at a time: their word
+        //         values are all requested before the first is used (the loads miss L2 more often than not: the planes that
+        //         stream through it have pushed the word arrays out).
+        {
+            const uint32_t j = (uint32_t)lane;
+            uint32_t oddbits = 0;
+            // (a full tile without rows for the general path -- nearly every tile -- runs without the per-row tests)
+            auto assemble = [&](auto guarded) {
+                constexpr bool G = decltype(guarded)::value;
+                for (int dg = 0; dg < (G ? nd : 32); dg += 8) {
+                    uint32_t val[8];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t j = (uint32_t)(j0 + k), u = j - 1u;     // (j == 0: u wraps, not a word)
-                    inA[k] = u < nwA;
-                    inB[k] = PAIR && j >= b0 && j < e2;
-                    val[k] = 0u;
-                    if (inA[k]) val[k] = A.a.wtok[flat_word_index(A.a, baseA, availA, u)];
-                    if (PAIR && inB[k]) val[k] = A.b.wtok[flat_word_index(A.b, baseB, availB, j - b0)];
-                }
-                int32_t t[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int32_t j = j0 + k;
-                    // <s> A </s> [</s> B </s>] pad...   (tokenize.py:135,237-239,141-146)
-                    int32_t v = j == 0 ? T.bos : (j < Lr ? T.eos : T.pad);
-                    if (inA[k] || (PAIR && inB[k])) {
-                        v = (int32_t)(val[k] & VAL_PAYLOAD);
-                        if ((val[k] & VAL_KIND) != VAL_SINGLE) odd = true;
-                        else if (v <= spec_max && (v == T.eos || v == T.bos || v == T.pad)) special = true;
+                    for (int k = 0; k < 8; k++) {
+                        const int d = dg + k;
+                        val[k] = VAL_SINGLE;
+                        if (!G || (d < nd && !((slow_rows >> d) & 1u))) {
+                            const uint4 fa = ts->fa[d];
+                            const uint32_t L = ts->fc[d].x;
+                            const bool a = (j - 1u) < (fa.w - 1u);
+                            uint32_t idx = j + (j < fa.z ? fa.x : fa.y);
+                            bool inw = a;
+                            if (PAIR) {
+                                const uint4 fb = ts->fb[d];
+                                const uint32_t bc0 = fa.w + 2u;
+                                const bool b = (j - bc0) < (fb.w - bc0);
+                                const uint32_t idxb = j + (j < fb.z ? fb.x : fb.y);
+                                idx = a ? idx : idxb;
+                                inw = a | b;
+                            }
+                            // <s> A </s> [</s> B </s>] pad...   (tokenize.py:135,237-239,141-146)
+                            val[k] = VAL_SINGLE | (uint32_t)(j == 0 ? T.bos : (j < L ? T.eos : T.pad));
+                            if (inw) val[k] = wtok[idx];
+                        }
                     }
-                    t[k] = v;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int d = dg + k;
+                        if (!G || d < nd) {
+                            oddbits |= (uint32_t)((val[k] >> 30) != 1u) << d;   // not "one token": its BPE was pending at look-up, or several tokens
+                            ts->stage[d][lane] = val[k] & VAL_PAYLOAD;
+                        }
+                    }
                 }
-                if (cut && j0 + 4 == W) t[3] = T.eos;
-                st_cs128(A.ids + grow + j0, make_uint4((uint32_t)t[0], (uint32_t)t[1], (uint32_t)t[2], (uint32_t)t[3]));
-                st_cs32(A.mask + grow + j0, mask_word(Lr - j0));
-                if (PAIR && want_tt) {
-                    uint32_t ttw, sqw;
-                    const int32_t lo1 = ts->tlo[d];
-                    if (lo1 >= 0) ttw = mask_word(ts->dsd[d].m - j0) & ~mask_word(lo1 - j0);
-                    else seq_words4(ts->dsd[d], j0, W, A.eos_i8, &ttw, &sqw);
-                    st_cs32(A.tt + grow + j0, ttw);
-                }
-            }
-            (void)a1;
-            // a word that is not a single token: the positions need the token counts -- the whole warp rebuilds such rows
-            uint32_t odd_rows = __ballot_sync(FULL_MASK, odd);
-            const uint32_t special_rows = __ballot_sync(FULL_MASK, special);
-            if (special_rows && lane < 8) {
-                const int dd = dg + lane;
-                if (dd < nd && ((special_rows >> (4 * lane)) & 0xFu)) ts->dflag[dd] = FF_AGAIN;
-            }
-            while (odd_rows) {
-                const int dr = ((__ffs(odd_rows) - 1) >> 2);
-                odd_rows &= ~(0xFu << (4 * dr));
-                const int dd = dg + dr;
-                __syncwarp();
-                for (int32_t j = lane; j < KR; j += 32) rebuild[j] = T.pad;
-                __syncwarp();
-                if (lane == 0 && cap > 0) rebuild[0] = T.bos;
-                uint32_t flags = 0;
-                int32_t pos = flat_side_tokens(T, C, A.a, ts->base[0][dd], ts->avail[0][dd], ts->nw[0][dd], 1, limit, cap, rebuild, lane, &flags);
-                const int32_t nA = pos - 1;
-                if (pair) {
-                    if (lane == 0) { if (pos < cap) rebuild[pos] = T.eos; if (pos + 1 < cap) rebuild[pos + 1] = T.eos; }
-                    pos = flat_side_tokens(T, C, A.b, ts->base[1][dd], ts->avail[1][dd], ts->nw[1][dd], pos + 2, limit, cap, rebuild, lane, &flags);
-                }
-                const int32_t dL = pos + 1;
-                if (lane == 0) { if (pos < cap) rebuild[pos] = T.eos; if (dL >= W && W - 1 < KR) rebuild[W - 1] = T.eos; }
-                flags = __reduce_or_sync(FULL_MASK, flags);
-                SeqDesc sd;
-                if (pair) sd = seq_describe(nA, dL, W);
-                if (lane == 0) { ts->dnA[dd] = nA; ts->dL[dd] = dL; ts->dflag[dd] |= flags; if (pair) { ts->dsd[dd] = sd; ts->tlo[dd] = -1; } }
-                __syncwarp();
-                const int32_t Lr2 = min(dL, W);
-                const size_t g2 = (size_t)(r0 + dd) * (size_t)W;
-                for (int32_t q = lane; q < qpr; q += 32) {
-                    const int4 v = *reinterpret_cast<const int4*>(rebuild + q * 4);
-                    st_cs128(A.ids + g2 + q * 4, make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w));
-                    st_cs32(A.mask + g2 + q * 4, mask_word(Lr2 - q * 4));
-                    if (want_tt) { uint32_t ttw, sqw; seq_words4(sd, q * 4, W, A.eos_i8, &ttw, &sqw); st_cs32(A.tt + g2 + q * 4, ttw); }
-                }
-            }
+            };
+            if (nd == 32 && slow_rows == 0u) assemble(std::false_type{}); else assemble(std::true_type{});
+            slow_rows |= __reduce_or_sync(FULL_MASK, oddbits);
         }
         __syncwarp();
-        // ---- 3. row bookkeeping (one lane per row)
+        // ---- 3. the planes of the usual rows, a lane per 16 bytes
+        auto write_out = [&](auto guarded) {
+            constexpr bool G = decltype(guarded)::value;
+            const size_t g0 = (size_t)r0 * (size_t)W;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {                               // ids, columns 0..31: 8 lanes per row
+                const int d = it * 4 + (lane >> 3), q = lane & 7;
+                if (!G || (d < nd && !((slow_rows >> d) & 1u)))
+                    st_cs128(A.ids + g0 + (size_t)(d * W + q * 4), *reinterpret_cast<const uint4*>(&ts->stage[d][q * 4]));
+            }
+            for (int32_t c0 = 32; c0 < KR; c0 += 32) {                     // ids, the other staged columns: pad ids
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int d = it * 4 + (lane >> 3);
+                    const int32_t col = c0 + (lane & 7) * 4;
+                    if ((!G || (d < nd && !((slow_rows >> d) & 1u))) && col < KR) st_cs128(A.ids + g0 + (size_t)(d * W + col), pad4);
+                }
+            }
+            for (int32_t c0 = 0; c0 < KR; c0 += 64) {                      // mask and token types: 4 lanes per row and pass
+#pragma unroll
+                for (int it = 0; it < 4; it++) {
+                    const int d = it * 8 + (lane >> 2);
+                    const int32_t col = c0 + (lane & 3) * 16;
+                    if ((!G || (d < nd && !((slow_rows >> d) & 1u))) && col < KR) {
+                        const uint4 fc = ts->fc[d];
+                        const size_t g = g0 + (size_t)(d * W + col);
+                        st_cs128(A.mask + g, s_ones[min(max((int32_t)fc.x - col, 0), 16)]);
+                        if (want_tt) {
+                            const uint4 hi1 = s_ones[min(max((int32_t)fc.z - col, 0), 16)], lo1 = s_ones[min(max((int32_t)fc.y - col, 0), 16)];
+                            st_cs128(A.tt + g, make_uint4(hi1.x & ~lo1.x, hi1.y & ~lo1.y, hi1.z & ~lo1.z, hi1.w & ~lo1.w));
+                        }
+                    }
+                }
+            }
+        };
+        if (nd == 32 && slow_rows == 0u && KR >= 32) write_out(std::false_type{}); else if (KR >= 32) write_out(std::true_type{});
+        // ---- 4. the other rows: the whole warp rebuilds each through a token scan
+        slow_rows &= nd >= 32 ? 0xFFFFFFFFu : ((1u << nd) - 1u);
+        while (slow_rows) {
+            const int d = __ffs(slow_rows) - 1;
+            slow_rows &= slow_rows - 1;
+            __syncwarp();
+            const uint4 fa = ts->fa[d];
+            const uint4 fb = PAIR ? ts->fb[d] : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t nwA = fa.w - 1u, bc0 = fa.w + 2u;
+            const size_t grow = (size_t)(r0 + d) * (size_t)W;
+            __syncwarp();
+            for (int32_t j = lane; j < KR; j += 32) rebuild[j] = T.pad;
+            __syncwarp();
+            if (lane == 0 && cap > 0) rebuild[0] = T.bos;
+            uint32_t flags = 0;
+            int32_t pos = flat_side_tokens(T, C, A.a, fa.x + 1u, fa.z - 1u, nwA, 1, limit, cap, rebuild, lane, &flags);
+            const int32_t nA = pos - 1;
+            if (pair) {
+                if (lane == 0) { if (pos < cap) rebuild[pos] = T.eos; if (pos + 1 < cap) rebuild[pos + 1] = T.eos; }
+                pos = flat_side_tokens(T, C, A.b, fb.x - segB + bc0, fb.z - bc0, fb.w - bc0, pos + 2, limit, cap, rebuild, lane, &flags);
+            }
+            const int32_t dL = pos + 1;
+            if (lane == 0) { if (pos < cap) rebuild[pos] = T.eos; if (dL >= W && W - 1 < KR) rebuild[W - 1] = T.eos; }
+            flags = __reduce_or_sync(FULL_MASK, flags);
+            SeqDesc sd;
+            sd.m = 0; sd.err = 0;
+            if (pair) sd = seq_describe(nA, dL, W);
+            __syncwarp();
+            const int32_t Lr2 = min(dL, W);
+            for (int32_t q = lane; q < KQ; q += 32) {
+                const int4 t4 = *reinterpret_cast<const int4*>(rebuild + q * 4);
+                st_cs128(A.ids + grow + q * 4, make_uint4((uint32_t)t4.x, (uint32_t)t4.y, (uint32_t)t4.z, (uint32_t)t4.w));
+                st_cs32(A.mask + grow + q * 4, mask_word(Lr2 - q * 4));
+                if (want_tt) { uint32_t ttw, sqw; seq_words4(sd, q * 4, W, A.eos_i8, A.pad_i8, &ttw, &sqw); st_cs32(A.tt + grow + q * 4, ttw); }
+            }
+            __syncwarp();
+            if (lane == 0) ts->fc[d] = make_uint4((uint32_t)dL, 0xFFFFFFFFu, (uint32_t)sd.m, (flags & FF_AGAIN) | (sd.err ? FR_ERR : 0u));
+        }
+        __syncwarp();
+        // ---- 5. row bookkeeping (one lane per row)
         if (lane < nd) {
-            const int32_t dL = ts->dL[lane];
-            const uint32_t fl = ts->dflag[lane];
-            const bool again = (fl & FF_AGAIN) || (KR < W && (dL > KR || (pair && ts->dsd[lane].m > KR)));
+            const uint4 fc = ts->fc[lane];
+            const int32_t dL = (int32_t)fc.x, m = (int32_t)fc.z;
+            const bool again = (fc.w & FF_AGAIN) || (KR < W && (dL > KR || (pair && m > KR)));
             if (again) {
                 const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL);
                 A.redo_list[k] = (uint32_t)(r0 + lane);
@@ -728,14 +797,14 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                 if (A.row_len) A.row_len[dr] = Lr;
                 tok_total += (uint32_t)Lr;
                 if (pair) {
-                    if (A.seq_len) A.seq_len[dr] = ts->dsd[lane].m;
-                    if (A.status) A.status[dr] = (uint8_t)ts->dsd[lane].err;
+                    if (A.seq_len) A.seq_len[dr] = m;
+                    if (A.status) A.status[dr] = (uint8_t)((fc.w & FR_ERR) ? 1 : 0);
                 }
             }
         }
         __syncwarp();
     }
-    if (lane == 0) bulk_wait<0>();          // the constant buffer must outlive the tensor stores that read it
+    if (PB && lane == 0) bulk_wait<0>();          // the constant buffer must outlive the tensor stores that read it
     __syncwarp();
     tok_total = __reduce_add_sync(FULL_MASK, tok_total);
     if (lane == 0 && tok_total) atomicAdd(&C.ctr[C_TOKENS], (unsigned long long)tok_total);

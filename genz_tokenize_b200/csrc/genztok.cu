@@ -76,7 +76,7 @@ struct DeviceCtx {
     DevBuf tok_flag, tok_len, tok_pos;            // decode of ragged rows by id: last-of-row flags, bytes per id, their scan
     int64_t tok_base = 0, tok_n = -1;             // the ids that scan describes
     struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; int by_id = 0; } dec_sig;   // the batch it describes
-    struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok, fixa, fixp; } flat[2];   // byte-parallel pipeline, per side
+    struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok; } flat[2];   // byte-parallel pipeline, per side
     // the shared work areas (word cache, lists, flat arrays) are used by one stream at a time: a call on another stream
     // first waits for the event the previous call left behind
     cudaEvent_t last_done = nullptr;
@@ -110,8 +110,11 @@ struct genztok {
     int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
+    int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
+    int64_t l2_policy = 0;               // bit 0: text read evict-first, bit 1: word arrays stored evict-last (k_flat_words; experiments)
+    int64_t rows_pad_pct = 0;            // share of the pad columns (percent of the 32-row tiles, the last ones) that k_flat_rows stores instead of k_flat_words
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
-    int64_t rows_minb = 5, words_minb = 4;   // resident 256-thread blocks per SM the flat kernels are compiled for (4, 5 or 6)
+    int64_t rows_minb = 0, words_minb = 3;   // resident 256-thread blocks per SM the flat kernels are compiled for (rows: 0 = 3 for pairs, 5 for single sentences)
     int64_t no_tma = 0;                  // write the fixed planes with store instructions instead of the TMA unit (test knob)
     int64_t no_token_decode = 0;         // decode ragged rows with a warp per row instead of a thread per id (test knob)
     int64_t no_fixed_decode = 0;         // decode fixed-width rows with the any-rows kernels (test knob)
@@ -358,8 +361,12 @@ bool setup_tma(genztok_t* h, const DeviceCtx* d, const RowArgs& A, int64_t bytes
     if (KR <= 0) KR = std::max<int64_t>(32, (bytes / A.n_rows / 3 + 12 + (A.has_pair ? 4 : 0) + 15) & ~15ll);
     if (KR + 16 > W) KR = W;
     if (KR > 256) return false;
-    const int32_t PB = (int32_t)std::min<int64_t>(W - KR, 256);
+    // columns per pad box: the constant buffer a block keeps for it costs shared memory (hence L1) in proportion
+    int32_t PB = (int32_t)std::min<int64_t>(W - KR, 256);
+    if (tile_bytes != sizeof(TileSmem) && h->pad_box_cols > 0 && PB > h->pad_box_cols)
+        for (int32_t pb = (int32_t)h->pad_box_cols; pb >= 16; pb -= 16) if ((W - KR) % pb == 0) { PB = pb; break; }   // the widest box that tiles the pad columns
     const bool tt = A.has_pair && A.tt;
+    if (tt && A.pad_i8 != 0) return false;      // the constant pad boxes of token_type_ids are zeros: a pad id that is not 0 takes the store path
     if (tile_bytes == sizeof(TileSmem)) {
         // the fused kernel is latency bound: the staging must not cost occupancy (four 8-warp blocks per SM), else the store path wins
         if (!h->force_kr && 4 * ((PB ? tma_const_bytes(A.D, PB) : 0) + 8 * (r128(tile_bytes) + 2 * tma_stage_bytes(A.D, (int)KR, tt)) + 1024) > d->smem_per_sm) return false;
@@ -422,21 +429,30 @@ int launch_scan(genztok_t* h, DeviceCtx* d, cudaStream_t st, const int64_t* in, 
     return GENZTOK_OK;
 }
 
+int8_t pad_as_i8(const DeviceCtx* d) { return (d->T.pad >= 0 && d->T.pad <= 127) ? (int8_t)d->T.pad : (int8_t)GENZTOK_PAD_MARK; }
 int8_t eos_as_i8(const DeviceCtx* d) { return (d->T.eos >= 0 && d->T.eos <= 127) ? (int8_t)d->T.eos : (int8_t)GENZTOK_EOS_MARK; }
 
 // work arrays of the byte-parallel pipeline for one side (flat.cuh)
-int flat_side_setup(genztok_t* h, DeviceCtx* d, int s, const Side& side, int64_t n, FlatSide* out) {
+uint64_t flat_chunks(int64_t nbytes) {
+    const uint64_t nG = (((uint64_t)nbytes + 15) >> 5) + 3;                 // granules (+ slack for the clamp in flat_hi)
+    return (nG + FC_OWN - 1) / FC_OWN + 1;                                   // chunks
+}
+// (the word arrays of both sides are one allocation, side B's behind side A's: k_flat_rows addresses them with one base pointer)
+int flat_side_setup(genztok_t* h, DeviceCtx* d, int s, const Side& side, const Side* other, int64_t n, FlatSide* out) {
     DeviceCtx::FlatBufs& B = d->flat[s];
-    const uint64_t nG = (((uint64_t)side.nbytes + 15) >> 5) + 3;            // granules (+ slack for the clamp in flat_hi)
-    const uint64_t nB = (nG + FC_OWN - 1) / FC_OWN + 1;                      // chunks
-    const uint64_t fix_cap = std::min<uint64_t>(nB * FC_BYTES, ((uint64_t)side.nbytes + (uint64_t)n) / 2 + 64);
+    const uint64_t nB = flat_chunks(side.nbytes);
     const uint64_t ng = nB * FC_OWN + 2;
     CU(B.dsb.ensure(ng * 4)); CU(B.st.ensure(ng * 4)); CU(B.tpref.ensure(ng * 2));
-    CU(B.cnt.ensure(nB * 4)); CU(B.wtok.ensure((nB << FC_SHIFT) * 4)); CU(B.fixa.ensure(fix_cap * 4)); CU(B.fixp.ensure(fix_cap * 4));
+    CU(B.cnt.ensure(nB * 4));
+    if (s == 0) {
+        const uint64_t all = nB + (other ? flat_chunks(other->nbytes) : 0);
+        if ((all << FC_SHIFT) >= (1ull << 32)) return fail(h, GENZTOK_E_LIMIT, "chunk too large for the byte-parallel pipeline");
+        CU(B.wtok.ensure((all << FC_SHIFT) * 4));
+    }
     out->bytes = side.bytes; out->off = side.off; out->n = n;
     out->dsb = B.dsb.as<uint32_t>(); out->st = B.st.as<uint32_t>(); out->tpref = B.tpref.as<uint16_t>(); out->cnt = B.cnt.as<uint32_t>();
-    out->wtok = B.wtok.as<uint32_t>(); out->fixa = B.fixa.as<uint32_t>(); out->fixp = B.fixp.as<uint32_t>();
-    out->fix_cap = (uint32_t)fix_cap; out->ctr_fix = s ? C_FLATFIX_B : C_FLATFIX_A; out->nB = (uint32_t)nB;
+    out->wtok = s == 0 ? B.wtok.as<uint32_t>() : d->flat[0].wtok.as<uint32_t>() + (flat_chunks(other->nbytes) << FC_SHIFT);
+    out->nB = (uint32_t)nB;
     return GENZTOK_OK;
 }
 
@@ -464,6 +480,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     A.row_len = P.row_len; A.seq_len = P.seq_len; A.status = P.row_status;
     A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>();
     A.eos_i8 = eos_as_i8(d);
+    A.pad_i8 = pad_as_i8(d);
     A.D = pick_tile_docs(h, d, a.nbytes, b ? b->nbytes : 0, n, W, true);
     TmaPlanes M;
     // The byte-parallel pipeline (flat.cuh) when the rows are short enough that every word matters; the fused row
@@ -477,11 +494,11 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         if (flat) {
             FlatRowsArgs F{};
             for (int s = 0; s < (b ? 2 : 1); s++) {
-                rc = flat_side_setup(h, d, s, s ? *b : a, n, s ? &F.b : &F.a);
+                rc = flat_side_setup(h, d, s, s ? *b : a, s ? &a : b, n, s ? &F.b : &F.a);
                 if (rc) return rc;
             }
             F.has_pair = b != nullptr; F.n_rows = n; F.W = W; F.D = Af.D; F.ids = A.ids; F.mask = A.mask; F.tt = A.tt;
-            F.row_len = A.row_len; F.seq_len = A.seq_len; F.status = A.status; F.redo_list = A.redo_list; F.fix_list = A.fix_list; F.eos_i8 = A.eos_i8;
+            F.row_len = A.row_len; F.seq_len = A.seq_len; F.status = A.status; F.redo_list = A.redo_list; F.fix_list = A.fix_list; F.eos_i8 = A.eos_i8; F.pad_i8 = A.pad_i8;
             // cache guard / clear; the document-start bitmaps are zeroed by the same launch
             rc = launch_guard(h, d, st, bytes + 16, 0, F.a.dsb, (uint64_t)F.a.nB * FC_OWN + 2, b ? F.b.dsb : nullptr, b ? (uint64_t)F.b.nB * FC_OWN + 2 : 0);
             if (rc) return rc;
@@ -501,42 +518,63 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 const bool okp = setup_tma(h, d, Ap, bytes, &Mp, sizeof(FlatTile)) && Mp.KR == M.KR && Mp.PB == M.PB;
                 h->force_kr = keep_kr;
                 if (okp) {
-                    J.on = 1; J.n_tiles = (int32_t)((n + 31) / 32); J.W = W; J.D = 32; J.KR = Mp.KR; J.PB = Mp.PB;
+                    // rows_pad_pct percent of the pad tiles are left to k_flat_rows (which then needs 32-row tiles too)
+                    const int64_t all_tiles = (n + 31) / 32;
+                    const int64_t keep = F.D == 32 ? all_tiles * std::min<int64_t>(100, std::max<int64_t>(0, h->rows_pad_pct)) / 100 : 0;
+                    J.on = 1; J.n_tiles = (int32_t)(all_tiles - keep); J.W = W; J.D = 32; J.KR = Mp.KR; J.PB = Mp.PB;
                     J.want_tt = (F.has_pair && F.tt) ? 1 : 0; J.pad_id = d->T.pad;
                 }
             }
             static const TmaPlanes no_planes{};
-            for (int s = 0; s < (b ? 2 : 1); s++) {
-                const FlatSide& S = s ? F.b : F.a;
-                const bool pads = J.on != 0;                          // every launch takes its share of the pad tiles
-                PadJob Js = J;
-                if (b) { const int32_t half = J.n_tiles / 2; Js.tile0 = s ? half : 0; Js.n_tiles = s ? J.n_tiles - half : half; }
-                // algorithmic bytes: this side's text, and the pad columns it stores on the side (rows x (W - KR) x (4 + 1 [+ 1]))
-                const int64_t pad_rows = pads ? std::min<int64_t>(n - (int64_t)Js.tile0 * 32, (int64_t)Js.n_tiles * 32) : 0;
-                LaunchScope ls(h, d, "k_flat_words", (s ? b->nbytes : a.nbytes) + pad_rows * (int64_t)(W - J.KR) * (5 + J.want_tt));
+            {
+                // one launch walks both sides: the resident blocks are split between them in proportion to their chunks
+                const bool pads = J.on != 0;                          // every side takes its share of the pad tiles
+                FlatWordsArgs WA{};
+                auto wk = h->words_minb == 3 ? k_flat_words<3, 1> : (h->words_minb == 2 ? k_flat_words<2, 1> : (h->words_minb == 5 ? k_flat_words<5, 1> : k_flat_words<4, 1>));
+                const int64_t wmb = h->words_minb;
+                const uint64_t resident = (uint64_t)d->sm_count * (uint64_t)std::max<int64_t>(1, wmb) * (8 / FW_WARPS);
+                const uint64_t need_a = ((uint64_t)F.a.nB + FW_WARPS - 1) / FW_WARPS, need_b = b ? ((uint64_t)F.b.nB + FW_WARPS - 1) / FW_WARPS : 0;
+                uint64_t blocks_a = need_a, blocks_b = need_b;
+                if (need_a + need_b > resident) {
+                    blocks_a = b ? std::max<uint64_t>(1, resident * need_a / (need_a + need_b)) : resident;
+                    blocks_b = b ? std::max<uint64_t>(1, resident - blocks_a) : 0;
+                    blocks_a = std::min(blocks_a, need_a); blocks_b = std::min(blocks_b, need_b);
+                }
+                int64_t alg = 0;
+                for (int s = 0; s < (b ? 2 : 1); s++) {
+                    const FlatSide& S = s ? F.b : F.a;
+                    PadJob Js = J;
+                    if (b) {   // pad tiles in proportion to the side's share of the blocks
+                        const int32_t first = (int32_t)((int64_t)J.n_tiles * (int64_t)blocks_a / (int64_t)(blocks_a + blocks_b));
+                        Js.tile0 = s ? first : 0; Js.n_tiles = s ? J.n_tiles - first : first;
+                    }
+                    // algorithmic bytes: this side's text, and the pad columns it stores on the side (rows x (W - KR) x (4 + 1 [+ 1]))
+                    const int64_t pad_rows = pads ? std::max<int64_t>(0, std::min<int64_t>(n - (int64_t)Js.tile0 * 32, (int64_t)Js.n_tiles * 32)) : 0;
+                    alg += (s ? b->nbytes : a.nbytes) + pad_rows * (int64_t)(W - J.KR) * (5 + J.want_tt);
+                    Js.l2_policy = (int32_t)h->l2_policy;
+                    Js.ratio = (uint32_t)((((uint64_t)std::max<int32_t>(Js.n_tiles, 0) << 20) + S.nB - 1) / S.nB);
+                    WA.side[s] = S; WA.job[s] = Js;
+                }
+                WA.blocks_a = (uint32_t)blocks_a; WA.insert_ok = 1;
+                LaunchScope ls(h, d, "k_flat_words", alg);
                 const size_t dsm = pads ? tma_const_bytes(J.D, J.PB) : 0;
-                auto wk = h->words_minb == 3 ? k_flat_words<3, 2> : (h->words_minb == 14 ? k_flat_words<4, 2> : (h->words_minb == 5 ? k_flat_words<5, 1> : k_flat_words<4, 1>));
-                const int64_t wmb = h->words_minb == 14 ? 4 : h->words_minb;
-                const unsigned per_sm = (unsigned)std::max<int64_t>(1, wmb) * (8 / FW_WARPS);
-                const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)S.nB + FW_WARPS - 1) / FW_WARPS, (uint64_t)d->sm_count * per_sm);
                 if (dsm) CU(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                CU(launch_pdl(wk, dim3(grid), dim3(FW_WARPS * 32), dsm, st, d->T, d->C, S, 1, Js, pads ? Mp : no_planes));
+                CU(launch_pdl(wk, dim3((unsigned)(blocks_a + blocks_b)), dim3(FW_WARPS * 32), dsm, st, d->T, d->C, WA, pads ? Mp : no_planes));
                 CU(cudaGetLastError());
             }
-            if (J.on) M.PB = 0;                                       // k_flat_rows: real columns only
+            // k_flat_rows stores the pad columns of the tiles the side job does not cover (all of them without a side job)
+            F.pad_tile0 = J.on ? (uint32_t)J.n_tiles : 0u;
+            if (J.on && (int64_t)J.n_tiles >= (n + 31) / 32) M.PB = 0;    // none left: real columns only
             CU(cudaGetLastError());
             rc = launch_bpe(h, d, st);
             if (rc) return rc;
-            for (int s = 0; s < (b ? 2 : 1); s++) {
-                const FlatSide& S = s ? F.b : F.a;
-                LaunchScope ls(h, d, "k_flat_fix"); CU(launch_pdl(k_flat_fix, dim3(d->sm_count * 2), dim3(256), 0, st, d->C, S));
-            }
             {
                 const bool tt = F.has_pair && F.tt;
-                const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * (r128(sizeof(FlatTile)) + r128((size_t)M.KR * 4));
+                const size_t smem = (M.PB ? tma_const_bytes(F.D, M.PB) : 0) + 8 * r128(sizeof(FlatTile));
                 // (the pair instantiation needs its 63 registers: 4 blocks per SM unless asked otherwise)
-                auto kern = F.has_pair ? (h->rows_minb == 6 ? k_flat_rows<6, true> : (h->rows_minb == 15 ? k_flat_rows<5, true> : k_flat_rows<4, true>))
-                                       : (h->rows_minb == 8 ? k_flat_rows<8, false> : (h->rows_minb == 6 ? k_flat_rows<6, false> : (h->rows_minb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>)));
+                const int64_t rmb = h->rows_minb ? h->rows_minb : (F.has_pair ? 3 : 5);
+                auto kern = F.has_pair ? (rmb == 3 ? k_flat_rows<3, true> : (rmb == 2 ? k_flat_rows<2, true> : k_flat_rows<4, true>))
+                                       : (rmb == 3 ? k_flat_rows<3, false> : (rmb == 2 ? k_flat_rows<2, false> : (rmb == 5 ? k_flat_rows<5, false> : k_flat_rows<4, false>)));
                 if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 1;
                 CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -545,7 +583,8 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 if (h->rows_grid > 0) occ = std::min<int>(occ, (int)h->rows_grid);
                 const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, (int64_t)d->sm_count * occ * h->grid_mult));
                 // algorithmic bytes: the document offsets in, the staged columns (and, without the side job, the pad columns) of every plane out
-                LaunchScope ls(h, d, "k_flat_rows", (int64_t)(b ? 2 : 1) * 8 * (n + 1) + n * (int64_t)(M.PB ? W : M.KR) * (5 + (tt ? 1 : 0)));
+                const int64_t own_pad_rows = M.PB ? std::max<int64_t>(0, n - (int64_t)F.pad_tile0 * 32) : 0;
+                LaunchScope ls(h, d, "k_flat_rows", (int64_t)(b ? 2 : 1) * 8 * (n + 1) + (n * (int64_t)M.KR + own_pad_rows * (int64_t)(W - M.KR)) * (5 + (tt ? 1 : 0)));
                 CU(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, d->T, d->C, F, M));
             }
             CU(cudaGetLastError());
@@ -568,7 +607,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         PostArgs Q{};
         Q.ids = P.input_ids; Q.W = W; Q.n_rows = n; Q.row_list = d->fix.as<uint32_t>();
         Q.has_pair = 1; Q.tt = A.tt; Q.seq = A.seq; Q.seq_len = P.seq_len; Q.status = P.row_status;
-        Q.has_max_len = 1; Q.max_len = W; Q.padding = 1; Q.truncation = 1; Q.eos_i8 = A.eos_i8;
+        Q.has_max_len = 1; Q.max_len = W; Q.padding = 1; Q.truncation = 1; Q.eos_i8 = A.eos_i8; Q.pad_i8 = A.pad_i8;
         LaunchScope ls(h, d, "k_post_rows_fix");
         k_post_rows<<<d->sm_count, 256, 0, st>>>(d->T, Q, d->C.ctr + C_FIX);
         CU(cudaGetLastError());
@@ -655,7 +694,7 @@ void genztok_destroy(genztok_t* h) {
         for (auto e : d->free_events) cudaEventDestroy(e);
         if (d->last_done) cudaEventDestroy(d->last_done);
         d->synth_len.release();
-        for (auto& fb : d->flat) for (DevBuf* b : {&fb.dsb, &fb.st, &fb.tpref, &fb.cnt, &fb.wtok, &fb.fixa, &fb.fixp}) b->release();
+        for (auto& fb : d->flat) for (DevBuf* b : {&fb.dsb, &fb.st, &fb.tpref, &fb.cnt, &fb.wtok}) b->release();
         if (d->stream) cudaStreamDestroy(d->stream);
         delete d;
     }
@@ -732,6 +771,14 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->flat_rows = value;
     } else if (n == "no_side_pads") {
         h->no_side_pads = value;
+    } else if (n == "pad_box_cols") {
+        if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "pad_box_cols must be 0 or a multiple of 16 up to 256");
+        h->pad_box_cols = value;
+    } else if (n == "l2_policy") {
+        h->l2_policy = value;
+    } else if (n == "rows_pad_pct") {
+        if (value < 0 || value > 100) return fail(h, GENZTOK_E_INVALID, "rows_pad_pct must be in 0..100");
+        h->rows_pad_pct = value;
     } else if (n == "rows_grid") {
         h->rows_grid = value;
     } else if (n == "rows_minb") {
@@ -935,7 +982,7 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         FAIL_RC(launch_guard(h, d, st, tb + pb + 16, 0));
         RowArgs A{};
         A.a = a; A.b = b; A.has_pair = has_pair; A.n_rows = m; A.W = 0; A.flags = J.flags;
-        A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8;
+        A.L = d->L.as<int32_t>(); A.redo_list = d->redo.as<uint32_t>(); A.fix_list = d->fix.as<uint32_t>(); A.eos_i8 = eos8; A.pad_i8 = pad_as_i8(d);
         if (want_spans) {
             CUF(d->nwA.ensure((size_t)m * 4)); CUF(d->nwB.ensure((size_t)m * 4)); CUF(d->span_cnt.ensure((size_t)m * 8)); CUF(d->span_off.ensure((size_t)(m + 1) * 8));
             A.nwA = d->nwA.as<int32_t>(); A.nwB = d->nwB.as<int32_t>();
@@ -970,7 +1017,7 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         Q.ids = d->ids.as<int32_t>(); Q.row_off = d->row_off.as<int64_t>(); Q.n_rows = m; Q.keep = d->keep.as<int32_t>(); Q.tail = d->tail.as<uint8_t>();
         Q.mask = d->mask.as<uint8_t>(); Q.has_pair = has_pair; Q.row_len = d->row_len.as<int32_t>();
         if (has_pair) { Q.tt = d->tt.as<int8_t>(); Q.seq = d->seq.as<int8_t>(); Q.tt_len = d->tt_len.as<int32_t>(); Q.seq_len = d->seq_len.as<int32_t>(); Q.status = d->status.as<uint8_t>(); }
-        Q.has_max_len = has_max_len; Q.max_len = has_max_len ? max_len : 0; Q.padding = J.padding ? 1 : 0; Q.truncation = J.truncation ? 1 : 0; Q.eos_i8 = eos8;
+        Q.has_max_len = has_max_len; Q.max_len = has_max_len ? max_len : 0; Q.padding = J.padding ? 1 : 0; Q.truncation = J.truncation ? 1 : 0; Q.eos_i8 = eos8; Q.pad_i8 = pad_as_i8(d);
         Q.tokens_ctr = d->C.ctr + C_TOKENS;
         { LaunchScope ls(h, d, "k_post_rows"); k_post_rows<<<(unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)d->sm_count * 8), 256, 0, st>>>(d->T, Q, nullptr); }
         CUF(cudaGetLastError());
@@ -1557,7 +1604,7 @@ int genztok_sequence_id(genztok_t* h, const int32_t* ids, int64_t n, int apply_t
     CU(cudaMemcpyAsync(dids, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     PostArgs Q{};
     Q.ids = dids; Q.W = (int32_t)n; Q.n_rows = 1; Q.has_pair = 1; Q.seq = dseq; Q.seq_len = dlen; Q.status = dstat; Q.raw_seq = apply_token_type ? 0 : 1;
-    Q.eos_i8 = eos_as_i8(d);
+    Q.eos_i8 = eos_as_i8(d); Q.pad_i8 = pad_as_i8(d);
     { LaunchScope ls(h, d, "k_post_rows_helper"); k_post_rows<<<1, 32, 0, st>>>(d->T, Q, nullptr); }
     CU(cudaGetLastError());
     int32_t m = 0; uint8_t s8 = 0;

@@ -115,7 +115,7 @@ struct PostArgs {
     int32_t* tt_len; int32_t* seq_len; uint8_t* status; int32_t* row_len;
     int32_t has_max_len, max_len, padding, truncation;
     int32_t raw_seq;           // 1: write get_sequence_id's result without get_token_type (helper API)
-    int8_t eos_i8;
+    int8_t eos_i8, pad_i8;
     unsigned long long* tokens_ctr;   // += sum(mask)
 };
 
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_post_rows(DevTables T, PostArgs A, cons
             }
             if (A.seq) A.seq[start + i] = (int8_t)v;
             if (A.tt) {
-                int32_t tv = i < tt_keep ? v : (tt_tail == 2 && i == tt_keep ? (int32_t)A.eos_i8 : 0);
+                int32_t tv = i < tt_keep ? v : (tt_tail == 2 && i == tt_keep ? (int32_t)A.eos_i8 : (int32_t)A.pad_i8);
                 if (i < tt_len) A.tt[start + i] = (int8_t)tv;
             }
         }

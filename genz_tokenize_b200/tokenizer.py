@@ -335,8 +335,8 @@ class Tokenize(object):
         if r._has_pair:
             if r._status[i]:
                 raise ValueError("None is not in list")                   # tokenize.py:157-159
-            eos = self._special_ids()[2]
-            conv = lambda a: [None if v == L.NONE else (eos if v == L.EOS_MARK else int(v)) for v in a]
+            pad, _, eos = self._special_ids()[:3]
+            conv = lambda a: [None if v == L.NONE else (eos if v == L.EOS_MARK else (pad if v == L.PAD_MARK else int(v))) for v in a]
             seq = conv(r._seq[s:s + int(r._seq_len[i])])
             result['sequence_id'] = seq
             if r._pad_mode:

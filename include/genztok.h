@@ -47,6 +47,7 @@ extern "C" {
 /* Entries of the int8 planes */
 #define GENZTOK_NONE (-1)      /* Python None */
 #define GENZTOK_EOS_MARK (-3)  /* "the </s> id" when that id does not fit an int8 (tokenize.py:145 via :257) */
+#define GENZTOK_PAD_MARK (-4)  /* "the <pad> id" in token_type_ids when that id does not fit an int8 (tokenize.py:143 via :257) */
 
 typedef struct genztok genztok_t;
 

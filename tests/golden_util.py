@@ -21,6 +21,12 @@ def load_decode_golden():
         return json.loads(f.read().decode("ascii"))["blocks"]
 
 
+def load_padtt_golden():
+    """Reference pair calls with a pad token that is a vocab word -- pad id != 0 (oracle/gen_golden_padtt.py)."""
+    with gzip.open(os.path.join(HERE, "golden", "padtt_v1.json.gz"), "rb") as f:
+        return json.loads(f.read().decode("ascii"))["blocks"]
+
+
 def _norm(out):
     if "offset" in out:
         out = dict(out)

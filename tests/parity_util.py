@@ -13,7 +13,7 @@ def ragged_take(flat, starts, lens):
     return flat[idx]
 
 
-def assert_matches_oracle(be, orc, eos_id=2, what=""):
+def assert_matches_oracle(be, orc, eos_id=2, what="", pad_id=0):
     n = orc["n"]
     assert be._n == n
     olen = np.diff(orc["ids_off"])
@@ -51,7 +51,7 @@ def assert_matches_oracle(be, orc, eos_id=2, what=""):
         if be._pad_mode:
             tl = np.where(ok, be._tt_len, 0)
             ours = ragged_take(be._tt, starts, tl).astype(np.int32)
-            ours = np.where(ours == -3, eos_id, ours)
+            ours = np.where(ours == -3, eos_id, np.where(ours == -4, pad_id, ours))
             assert np.array_equal(tl, np.diff(orc["tt_off"])), "%s: token_type_ids lengths differ" % what
             bad = np.nonzero(ours != orc["tt"])[0]
             if len(bad):

@@ -711,3 +711,22 @@ def test_cuda_path_against_the_reference_itself(tok):
     ref_tok = ref_pool._tok
     for i in range(500):
         assert texts[i] == ref_tok.decode(be["input_ids"][i].tolist()), i
+
+
+def test_token_type_padding_is_the_pad_id(oracle):
+    """A pad token that is a vocab word (pad id != 0): token_type_ids is padded with the PAD ID (tokenize.py:256-258), the mask
+    compares with it (tokenize.py:148-152).  Reference vectors through the drop-in call, and a batch in the fixed layout (store
+    path: the TMA planes pad token types with zeros) against the oracle."""
+    from golden_util import load_padtt_golden
+    from genz_tokenize_b200 import Tokenize, workload
+    from genz_tokenize_b200.data import bundled_paths
+    from oracle.oracle import Oracle
+    v, b = bundled_paths()
+    for blk in load_padtt_golden():
+        t = Tokenize(pad_token=blk["pad_token"], devices=[0])
+        check_cases(t, blk["calls"], "pad token %r" % blk["pad_token"])
+        o = Oracle(v, b, [blk["pad_token"], None, None, None, None])
+        ta, tb = workload.generate_hashed(21, 0, 20000, 0, 3, 13, 0.02), workload.generate_hashed(21, 0, 20000, 1, 3, 13, 0.02)
+        for W in (48, 64):
+            be = t.encode_batch(ta, tb, max_len=W)
+            assert_matches_oracle(be, o.encode_batch(ta, tb, max_len=W, threads=8), pad_id=blk["pad_id"], what="pad token %r W=%d" % (blk["pad_token"], W))

@@ -178,3 +178,14 @@ def test_missing_file():
     from oracle.oracle import Oracle
     with pytest.raises(FileNotFoundError):
         Oracle("/nonexistent/vocab.txt", "/nonexistent/bpe.codes")
+
+
+def test_token_type_padding_is_the_pad_id():
+    """tokenize.py:256-258: token_type_ids is padded by __padding, i.e. with encoder[pad_token] -- reference vectors with pad ids 5 ... 15117."""
+    from golden_util import load_padtt_golden, check_cases
+    from oracle.oracle import Oracle
+    from genz_tokenize_b200.data import bundled_paths
+    v, b = bundled_paths()
+    for blk in load_padtt_golden():
+        o = Oracle(v, b, [blk["pad_token"], None, None, None, None])
+        check_cases(o, blk["calls"], "pad token %r" % blk["pad_token"])
