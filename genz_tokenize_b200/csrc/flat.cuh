@@ -222,8 +222,12 @@ struct FlatWordsArgs {
     uint32_t blocks_a;
     int32_t insert_ok;
 };
+// A block is FW_WARPS word warps and one pad warp: lane 0 of the pad warp issues the block's share of the pad boxes, paced by the
+// word warps' progress (at most FW_AHEAD chunk rounds ahead), so that no word warp ever waits for the TMA unit to take a store.
+static const int FW_THREADS = (FW_WARPS + 1) * 32;
+static const uint32_t FW_AHEAD = 1;
 template <int MINB, int ILP>
-__global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_words(DevTables T, WordCache C, const __grid_constant__ FlatWordsArgs P, const __grid_constant__ TmaPlanes M) {
+__global__ void __launch_bounds__(FW_THREADS, MINB) k_flat_words(DevTables T, WordCache C, const __grid_constant__ FlatWordsArgs P, const __grid_constant__ TmaPlanes M) {
     pdl_wait(); pdl_trigger();
     const int which = blockIdx.x >= P.blocks_a ? 1 : 0;
     const FlatSide& S = P.side[which];
@@ -232,14 +236,16 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
     const uint32_t block_id = blockIdx.x - (which ? P.blocks_a : 0u), n_blocks = which ? gridDim.x - P.blocks_a : P.blocks_a;
     __shared__ __align__(16) FlatWarpSmem s_warp[FW_WARPS];
     __shared__ uint4 s_keymask[17];                                          // byte masks of a 16-byte key by length
+    __shared__ uint32_t s_prog[FW_WARPS];                                    // chunk rounds each word warp has started
     extern __shared__ __align__(1024) uint8_t pad_smem[];                   // J.on: [D x PB] pad ids, [D x PB] zero bytes
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     if (tid < 17) {
         auto m32 = [&](int i) -> uint32_t { const int nb = min(max(tid - 4 * i, 0), 4); return nb ? (0xFFFFFFFFu >> (8 * (4 - nb))) : 0u; };
         s_keymask[tid] = make_uint4(m32(0), m32(1), m32(2), m32(3));
     }
+    if (tid < FW_WARPS) s_prog[tid] = 0u;
     __syncthreads();
-    FlatWarpSmem& sm = s_warp[wib];
+    FlatWarpSmem& sm = s_warp[wib < FW_WARPS ? wib : 0];
     uint32_t pad_s = 0, zeros_s = 0; uint64_t l2_first = 0;
     const uint64_t l2_last = l2_policy_evict_last();
     const uint64_t l2_stream = (J.l2_policy & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
@@ -275,7 +281,26 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
             ndsb = S.dsb[q0 >> 5];
         }
     };
+    if (wib == FW_WARPS) {                                                    // the pad warp
+        if (J.on && lane == 0) {
+            volatile uint32_t* prog = s_prog;
+            uint32_t round = 0;
+            for (uint32_t c0 = block_id * (uint32_t)FW_WARPS; c0 < S.nB; c0 += n_warps, round++) {
+                for (;;) {                                                    // stay at most FW_AHEAD rounds ahead of the slowest word warp
+                    uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int w = 0; w < FW_WARPS; w++) mn = min(mn, prog[w]);
+                    if (mn + FW_AHEAD > round) break;
+                    __nanosleep(200);
+                }
+                for (uint32_t w = 0; w < (uint32_t)FW_WARPS && c0 + w < S.nB; w++) flat_pad_tiles(J, M, c0 + w, S.nB, pad_s, zeros_s, l2_first);
+            }
+            bulk_wait<0>();                                                   // the constant buffer must outlive the tensor stores that read it
+        }
+        return;
+    }
     uint32_t c = block_id * (uint32_t)FW_WARPS + wib;
+    uint32_t round = 0;
     load_chunk(c);
     for (; c < S.nB; c += n_warps) {
         const uint4 v0 = nv0, v1 = nv1, v2 = nv2;
@@ -290,7 +315,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
         reinterpret_cast<uint4*>(text)[lane * 2 + 1] = v1;
         if (lane == 31) reinterpret_cast<uint4*>(text)[64] = v2;
         load_chunk(c + n_warps);                                              // next chunk's text: in flight during this chunk's work
-        if (J.on && lane == 0) flat_pad_tiles(J, M, c, S.nB, pad_s, zeros_s, l2_first);   // this chunk's share of the pad columns
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_prog[wib]) = ++round;      // (the pad warp follows)
 
         // whitespace bits of my bytes; bytes outside [lo, hi) are not text.  Usual text: a byte is whitespace iff it is
         // <= 0x20 (exact set only when a control character is around); a lead of a multi-byte whitespace (C2, E1..E3) is
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB * (8 / FW_WARPS)) k_flat_w
             st_keep32(&wtok[i], val, l2_keep);
         }
     }
-    if (J.on && lane == 0) bulk_wait<0>();      // the constant buffer must outlive the tensor stores that read it
+    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&s_prog[wib]) = 0xFFFFFFFFu - FW_AHEAD;   // done: the pad warp need not wait for me
     __syncwarp();
 }
 

@@ -532,7 +532,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 FlatWordsArgs WA{};
                 auto wk = h->words_minb == 3 ? k_flat_words<3, 1> : (h->words_minb == 2 ? k_flat_words<2, 1> : (h->words_minb == 5 ? k_flat_words<5, 1> : k_flat_words<4, 1>));
                 const int64_t wmb = h->words_minb;
-                const uint64_t resident = (uint64_t)d->sm_count * (uint64_t)std::max<int64_t>(1, wmb) * (8 / FW_WARPS);
+                const uint64_t resident = (uint64_t)d->sm_count * (uint64_t)std::max<int64_t>(1, wmb);
                 const uint64_t need_a = ((uint64_t)F.a.nB + FW_WARPS - 1) / FW_WARPS, need_b = b ? ((uint64_t)F.b.nB + FW_WARPS - 1) / FW_WARPS : 0;
                 uint64_t blocks_a = need_a, blocks_b = need_b;
                 if (need_a + need_b > resident) {
@@ -559,7 +559,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 LaunchScope ls(h, d, "k_flat_words", alg);
                 const size_t dsm = pads ? tma_const_bytes(J.D, J.PB) : 0;
                 if (dsm) CU(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-                CU(launch_pdl(wk, dim3((unsigned)(blocks_a + blocks_b)), dim3(FW_WARPS * 32), dsm, st, d->T, d->C, WA, pads ? Mp : no_planes));
+                CU(launch_pdl(wk, dim3((unsigned)(blocks_a + blocks_b)), dim3(FW_THREADS), dsm, st, d->T, d->C, WA, pads ? Mp : no_planes));
                 CU(cudaGetLastError());
             }
             // k_flat_rows stores the pad columns of the tiles the side job does not cover (all of them without a side job)
