@@ -368,6 +368,8 @@ def main():
     sampler.busy = True
 
     # ---- pass 0 (untimed as a step): cold word cache; digest of every plane; token count; no ValueError rows -----------
+    S.encode(0)                                                     # (the library's work areas are allocated by the first call: not part of "cold")
+    torch.cuda.synchronize()
     tok.cache_reset()
     acc = torch.zeros(1, dtype=torch.int64, device=dev)
     tok_acc = torch.zeros(1, dtype=torch.int64, device=dev)

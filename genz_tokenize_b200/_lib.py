@@ -21,7 +21,7 @@ class Encoded(C.Structure):
                 ("token_type_ids", C.POINTER(C.c_int8)), ("sequence_id", C.POINTER(C.c_int8)),
                 ("tt_len", C.POINTER(C.c_int32)), ("seq_len", C.POINTER(C.c_int32)),
                 ("row_status", C.POINTER(C.c_uint8)), ("span_off", C.POINTER(C.c_int64)),
-                ("spans", C.POINTER(C.c_int32)), ("real_tokens", C.c_int64), ("_owner", C.c_void_p)]
+                ("spans", C.POINTER(C.c_int32)), ("real_tokens", C.c_int64), ("_owner", C.c_void_p), ("d2h_bytes", C.c_int64)]
 
 
 class Text(C.Structure):

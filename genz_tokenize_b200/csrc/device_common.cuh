@@ -45,7 +45,7 @@ static const uint32_t SLOT_LOCKED = 0xFFFFFFFFu;
 static const uint32_t KEY_INLINE = 24;
 static const uint32_t VAL_PENDING = 0u, VAL_SINGLE = 1u << 30, VAL_MULTI = 2u << 30, VAL_KIND = 3u << 30, VAL_PAYLOAD = (1u << 30) - 1;
 
-enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_FLATFIX_A = 9, C_FLATFIX_B = 10, C_COUNT = 16 };
+enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_FLATFIX_A = 9, C_FLATFIX_B = 10, C_SCRATCH = 11, C_TICKET = 12, C_COUNT = 16 };
 
 struct WordCache {
     Slot* slots;
@@ -57,6 +57,8 @@ struct WordCache {
     uint32_t* pending;        // slot indices whose BPE has not run yet
     uint64_t pending_cap;
     unsigned long long* ctr;  // Counter[]
+    uint32_t* rank_scratch;   // k_bpe_pending: pair ranks of the long words of this call (bpe.cuh)
+    uint64_t rank_cap;
 };
 
 // Programmatic dependent launch: a kernel launched with the stream-serialization attribute may be scheduled while its
@@ -103,18 +105,26 @@ __device__ __forceinline__ uint32_t hash_key24(uint64_t k0, uint64_t k1, uint64_
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
     return h;
 }
-// 64-bit hash of a long key, 8 bytes at a time (unaligned bytes gathered bytewise only for the tail)
+// Bytes [p, p + 8) of a byte string at any alignment, out of aligned 8-byte loads: `lo` is the aligned word that holds p (the
+// caller keeps it from the previous step), `hi` the next one.  Reads stay inside [p & ~7, (p & ~7) + 16): every text buffer
+// is readable 16 bytes past its end (include/genztok.h), the key arena has the same slack.
+__device__ __forceinline__ uint64_t bytes8(uint64_t lo, uint64_t hi, uint32_t sh) { return sh ? (lo >> sh) | (hi << (64u - sh)) : lo; }
+// 64-bit hash of a long key, 8 bytes a step (one aligned load each)
 __device__ __forceinline__ uint64_t hash_long(const uint8_t* p, uint32_t len) {
-    uint64_t h = 0xcbf29ce484222325ULL ^ len;
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7) * 8u;
+    uint64_t h = 0xcbf29ce484222325ULL ^ len, lo = q[0];
     uint32_t i = 0;
     for (; i + 8 <= len; i += 8) {
-        uint64_t v = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) v |= (uint64_t)p[i + k] << (8 * k);
-        h = (h ^ v) * 0x9E3779B97F4A7C15ULL;
+        const uint64_t hi = *++q;
+        h = (h ^ bytes8(lo, hi, sh)) * 0x9E3779B97F4A7C15ULL;
         h ^= h >> 29;
+        lo = hi;
     }
-    for (; i < len; i++) { h ^= p[i]; h *= 0x100000001b3ULL; }
+    if (i < len) {
+        const uint64_t v = bytes8(lo, q[1], sh) & ((1ULL << ((len - i) * 8)) - 1);
+        h = (h ^ v) * 0x100000001b3ULL;
+    }
     return h ^ (h >> 32);
 }
 

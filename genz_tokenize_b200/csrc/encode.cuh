@@ -145,6 +145,16 @@ __device__ __forceinline__ uint32_t byte_of(const uint4& w, int j) {
     return (x >> ((j & 3) * 8)) & 0xFFu;
 }
 
+// Can any of these eight bytes end a word?  ASCII whitespace, or a lead of a multi-byte whitespace (C2, E1..E3) followed by a
+// byte in 0x80..0xA0 -- the next byte of the last one is not known and counts as one.  (Vietnamese letters are E1 BA / E1 BB xx,
+// C3 xx, C4 xx, C6 xx: they pass.)
+__device__ __forceinline__ bool may_end_word8(uint64_t v) {
+    const uint32_t x = (uint32_t)v, y = (uint32_t)(v >> 32);
+    const uint32_t lx = ws_lead4(x), ly = ws_lead4(y), sx = ws_second4(x), sy = ws_second4(y);
+    const uint32_t cand = (lx & __funnelshift_r(sx, sy, 8)) | (ly & ((sy >> 8) | 0x80000000u));
+    return (ascii_ws4(x) | ascii_ws4(y) | cand) != 0u;
+}
+
 // Length (2 or 3) of the non-ASCII whitespace code point whose lead byte b0 sits at position p, else 0.
 // The 19 non-ASCII members of \s: C2 85, C2 A0, E1 9A 80, E2 80 80..8A, E2 80 A8/A9/AF, E2 81 9F, E3 80 80.
 // (positions are 32-bit offsets from the tile base `tb`)
@@ -201,10 +211,17 @@ __device__ __forceinline__ uint32_t classify16(const uint4& w, const uint8_t* tb
 // First whitespace position at or after q (q is on a code point boundary or inside a non-ws one).
 __device__ __noinline__ int32_t slow_word_end(const uint8_t* tb, int32_t q, int32_t e) {
     while (q < e) {
-        uint32_t b = tb[q];
-        if (b <= 0x20) { if ((b >= 0x09 && b <= 0x0D) || b >= 0x1C) return q; }
-        else if (b >= 0xC2 && multibyte_ws(b, tb, q, e)) return q;
-        q++;
+        // eight bytes a step while none of them is ASCII whitespace or can start a multi-byte one (long tokens: URLs, base64, ...)
+        if (q + 8 <= e) {
+            const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(tb + q) & ~(uintptr_t)7);
+            const uint64_t v = bytes8(a[0], a[1], (uint32_t)(reinterpret_cast<uintptr_t>(tb + q) & 7) * 8u);
+            if (!may_end_word8(v)) { q += 8; continue; }
+        }
+        for (int k = 0; k < 8 && q < e; k++, q++) {
+            const uint32_t b = tb[q];
+            if (b <= 0x20) { if ((b >= 0x09 && b <= 0x0D) || b >= 0x1C) return q; }
+            else if (b >= 0xC2 && multibyte_ws(b, tb, q, e)) return q;
+        }
     }
     return e;
 }
@@ -302,17 +319,23 @@ __device__ __forceinline__ void key_mask24(uint32_t len, uint64_t* k0, uint64_t*
     *k2 &= ((uint64_t)m32(5) << 32) | m32(4);
 }
 
+// kp: a key in the arena (8-byte aligned, see the insert below), wptr: the word in the text (any alignment)
 __device__ __noinline__ bool long_key_equal(const uint8_t* kp, const uint8_t* wptr, uint32_t len) {
+    const uint64_t* k = reinterpret_cast<const uint64_t*>(kp);
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(wptr) & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(wptr) & 7) * 8u;
+    uint64_t lo = q[0];
     uint32_t i = 0;
-    for (; i + 8 <= len; i += 8) {                 // eight independent byte pairs per step (one round trip, not eight)
-        uint32_t diff = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) diff |= (uint32_t)kp[i + k] ^ (uint32_t)wptr[i + k];
-        if (diff) return false;
+    for (; i + 8 <= len; i += 8) {
+        const uint64_t hi = *++q;
+        if (bytes8(lo, hi, sh) != *k++) return false;
+        lo = hi;
     }
-    uint32_t diff = 0;
-    for (; i < len; i++) diff |= (uint32_t)kp[i] ^ (uint32_t)wptr[i];
-    return diff == 0;
+    if (i < len) {
+        const uint64_t m = (1ULL << ((len - i) * 8)) - 1;
+        if ((bytes8(lo, q[1], sh) ^ *k) & m) return false;
+    }
+    return true;
 }
 
 // Find the word in the cache or insert it (BPE pending).  Returns the slot's value word (VAL_*); for a word whose BPE has
@@ -340,10 +363,13 @@ __device__ __forceinline__ uint32_t cache_find_or_insert(const WordCache& C, con
             const uint32_t old = atomicCAS(&s->len, SLOT_EMPTY, SLOT_LOCKED);
             if (old != SLOT_EMPTY) continue;                 // lost the race: re-examine the same slot
             uint64_t v0 = k0;
-            if (len > KEY_INLINE) {
-                const uint64_t off = atomicAdd(&C.ctr[C_KEYS], (unsigned long long)len);
-                uint8_t* kp = C.key_arena + off;
-                for (uint32_t i = 0; i < len; i++) kp[i] = wptr[i];
+            if (len > KEY_INLINE) {                      // the key goes to the arena, 8-byte aligned, eight bytes a step
+                const uint64_t off = atomicAdd(&C.ctr[C_KEYS], (unsigned long long)((len + 7u) & ~7u));
+                uint64_t* kp = reinterpret_cast<uint64_t*>(C.key_arena + off);
+                const uint64_t* q = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(wptr) & ~(uintptr_t)7);
+                const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(wptr) & 7) * 8u;
+                uint64_t lo = q[0];
+                for (uint32_t i = 0; i < len; i += 8) { const uint64_t hi = *++q; *kp++ = bytes8(lo, hi, sh); lo = hi; }
                 v0 = off;
             }
             s->val = VAL_PENDING; s->k0 = v0; s->k1 = k1; s->k2 = k2;
@@ -551,7 +577,8 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                     const uint32_t kind = val & VAL_KIND;
                     if (kind == VAL_SINGLE) nt = 1;
                     else if (kind == VAL_MULTI) nt = C.tok_arena[val & VAL_PAYLOAD];
-                    else pending = true;                                // BPE not run yet (counts as 0 tokens for now)
+                    else { pending = true; nt = 1; }                    // BPE not run yet: at least one token (positions stay lower bounds, so a row
+                                                                        // still fills up and the walk can stop; the row is redone anyway)
                 }
             }
             // position of my first token: inclusive count of nt over the lanes of my document up to me
@@ -574,8 +601,13 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
             int32_t q = 0;
             if (has) q = ts->dpos[doc] + (int32_t)(sc - nt);
             // q is a lower bound of the word's position while earlier words are pending: if even that is past the
-            // row's end the word is irrelevant, otherwise the row must be redone after k_bpe_pending
-            if (pending && q < limit) atomicOr(&ts->dflag[doc], F_DIRTY);
+            // row's end the word is irrelevant, otherwise the row must be redone after k_bpe_pending (one lane per
+            // document says so: with a cold cache every word is pending)
+            {
+                const bool dirty = pending && q < limit;
+                const uint32_t dm = __ballot_sync(FULL_MASK, dirty);
+                if (dirty && (__ffs(dm >> seg0) - 1 + seg0 == lane)) atomicOr(&ts->dflag[doc], F_DIRTY);
+            }
             int wrank = 0, wbase_idx = 0;
             if (MODE != MODE_FIXED && count_words) {                     // word index inside the row (return_offset)
                 wrank = lane - seg0;
@@ -591,7 +623,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
                 e[0] = q + ts->rg.dshift[doc];
                 e[1] = q + (int32_t)nt - 1 + ts->rg.dshift[doc];
             }
-            if (MODE != MODE_COUNT && has && nt) {
+            if (MODE != MODE_COUNT && has && nt && !pending) {
                 TokT* dsts = nullptr; int32_t* dstg = nullptr; int32_t lim;
                 if (MODE == MODE_FIXED) { dsts = rowbufs + (size_t)doc * Wp; lim = cap; }
                 else { dstg = ids_out + ts->rg.dout[doc]; lim = ts->rg.dkeep[doc]; }

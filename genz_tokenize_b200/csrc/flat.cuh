@@ -70,12 +70,21 @@ __device__ __noinline__ bool flat_is_ws(const uint8_t* tb, const uint32_t* dsb, 
 // length of the word (\S+\n?) that starts at q: up to whitespace, a document start or the end of the text
 __device__ __noinline__ uint32_t flat_word_len(const uint8_t* tb, const uint32_t* dsb, uint32_t q, uint32_t hi) {
     uint32_t e = q + 1;
-    while (e < hi) {
-        if (dsb_bit(dsb, e)) return e - q;
-        const uint32_t b = tb[e];
-        if (b <= 0x20) { if (ascii_ws_byte(b)) break; }
-        else if (b >= 0xC2 && flat_mb_ws(tb, dsb, e, hi)) break;
-        e++;
+    bool ended = false;
+    while (e < hi && !ended) {
+        // eight bytes a step while none of them is ASCII whitespace, can start a multi-byte one, or starts a document (long tokens)
+        if (e + 8 <= hi) {
+            const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(tb + e) & ~(uintptr_t)7);
+            const uint64_t v = bytes8(a[0], a[1], (uint32_t)(reinterpret_cast<uintptr_t>(tb + e) & 7) * 8u);
+            const uint32_t d8 = __funnelshift_r(dsb[e >> 5], dsb[(e >> 5) + 1], e & 31u) & 0xFFu;
+            if (!may_end_word8(v) && !d8) { e += 8; continue; }
+        }
+        for (int k = 0; k < 8 && e < hi; k++, e++) {
+            if (dsb_bit(dsb, e)) return e - q;
+            const uint32_t b = tb[e];
+            if (b <= 0x20) { if (ascii_ws_byte(b)) { ended = true; break; } }
+            else if (b >= 0xC2 && flat_mb_ws(tb, dsb, e, hi)) { ended = true; break; }
+        }
     }
     if (e < hi && tb[e] == 0x0A && !dsb_bit(dsb, e)) e++;
     return e - q;
@@ -438,6 +447,22 @@ __global__ void __launch_bounds__(FW_THREADS, MINB) k_flat_words(DevTables T, Wo
                 if (!((a.x == len) & (a.z == k0) & (a.w == k1) & (b2.x == k2) & (b2.y == k3)))
                     val = cache_find_or_insert(C, tb + wq + p, len, ((uint64_t)k1 << 32) | k0, ((uint64_t)k3 << 32) | k2, 0ULL, h, insert_ok != 0);
                 else if ((val & VAL_KIND) == VAL_PENDING) val = VAL_PENDING | (h & C.mask);          // its BPE has not run: hand on the slot
+            } else if (len - 17u < 8u) {
+                // 17..24 bytes (glued or long compound words): the same from seven words of the staged text and both halves of the slot
+                const uint32_t* tw = reinterpret_cast<const uint32_t*>(text + (p & ~3u));
+                const uint32_t w0 = tw[0], w1 = tw[1], w2 = tw[2], w3 = tw[3], w4 = tw[4], w5 = tw[5], w6 = tw[6];
+                const uint32_t sh = (p & 3u) * 8u;
+                const uint4 mk = s_keymask[len - 16u];
+                const uint32_t k0 = __funnelshift_r(w0, w1, sh), k1 = __funnelshift_r(w1, w2, sh), k2 = __funnelshift_r(w2, w3, sh), k3 = __funnelshift_r(w3, w4, sh);
+                const uint32_t k4 = __funnelshift_r(w4, w5, sh) & mk.x, k5 = __funnelshift_r(w5, w6, sh) & mk.y;
+                const uint64_t K0 = ((uint64_t)k1 << 32) | k0, K1 = ((uint64_t)k3 << 32) | k2, K2 = ((uint64_t)k5 << 32) | k4;
+                const uint32_t h = hash_key24(K0, K1, K2, len);
+                const uint4* slot = reinterpret_cast<const uint4*>(&C.slots[h & C.mask]);
+                const uint4 a = ld_keep128(slot, l2_last), b4 = ld_keep128(slot + 1, l2_last);
+                val = a.y;
+                if (!((a.x == len) & (a.z == k0) & (a.w == k1) & (b4.x == k2) & (b4.y == k3) & (b4.z == k4) & (b4.w == k5)))
+                    val = cache_find_or_insert(C, tb + wq + p, len, K0, K1, K2, h, insert_ok != 0);
+                else if ((val & VAL_KIND) == VAL_PENDING) val = VAL_PENDING | (h & C.mask);
             } else val = flat_lookup_general(C, tb, S.dsb, wq + p, len, hi, insert_ok);
             st_keep32(&wtok[i], val, l2_keep);
         }
@@ -719,11 +744,14 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
                             if (inw) val[k] = wtok[idx];
                         }
                     }
+                    // a word whose BPE was pending at look-up (a cold cache: nearly all of them) has its value by now: one more load
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if ((val[k] >> 30) == 0u) val[k] = C.slots[val[k]].val;
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const int d = dg + k;
                         if (!G || d < nd) {
-                            oddbits |= (uint32_t)((val[k] >> 30) != 1u) << d;   // not "one token": its BPE was pending at look-up, or several tokens
+                            oddbits |= (uint32_t)((val[k] >> 30) != 1u) << d;   // not "one token": the row takes the general path
                             ts->stage[d][lane] = val[k] & VAL_PAYLOAD;
                         }
                     }

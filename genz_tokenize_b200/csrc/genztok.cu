@@ -71,12 +71,20 @@ struct DeviceCtx {
     DevBuf text, toff, pair, poff;                // inputs
     DevBuf ids, mask, tt, seq, row_len, seq_len, tt_len, status;   // outputs
     DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
-    DevBuf slots, key_arena, tok_arena, pending, ctr;
+    DevBuf slots, key_arena, tok_arena, pending, ctr, rank_scratch;
     DevBuf dec_lead;                              // decode: per-row description left by the length pass for the write pass
     DevBuf tok_flag, tok_len, tok_pos;            // decode of ragged rows by id: last-of-row flags, bytes per id, their scan
     int64_t tok_base = 0, tok_n = -1;             // the ids that scan describes
     struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; int by_id = 0; } dec_sig;   // the batch it describes
     struct FlatBufs { DevBuf dsb, st, tpref, cnt, wtok; } flat[2];   // byte-parallel pipeline, per side
+    // host path, fixed layout: two sets of chunk buffers so that the copy of chunk i + 1 to the device, the kernels of chunk i and
+    // the copy of chunk i - 1 to the host overlap (PCIe is full duplex); one stream each
+    struct Stage {
+        DevBuf text, toff, pair, poff, ids, mask, tt, seq, row_len, seq_len, status, extent;
+        cudaEvent_t h2d = nullptr, k = nullptr, d2h = nullptr;
+    } stage[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int32_t* h_extent = nullptr;                  // pinned: [2] staged-column extents of the two chunks in flight
     // the shared work areas (word cache, lists, flat arrays) are used by one stream at a time: a call on another stream
     // first waits for the event the previous call left behind
     cudaEvent_t last_done = nullptr;
@@ -103,7 +111,7 @@ struct genztok {
     std::mutex err_mu;                   // guards err / prof_names (device worker threads)
     // options
     int64_t max_chunk_bytes = 64ll << 20;
-    int64_t chunk_rows = 1ll << 20;
+    int64_t chunk_rows = 1ll << 18;     // rows per chunk of the host path: small enough that the copies of neighbouring chunks overlap the kernels
     int64_t force_group = 0;
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
@@ -111,6 +119,8 @@ struct genztok {
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
+    int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
+    int64_t copy_blocks = 64;            // blocks of k_copy_out
     int64_t l2_policy = 0;               // bit 0: text read evict-first, bit 1: word arrays stored evict-last (k_flat_words; experiments)
     int64_t rows_pad_pct = 0;            // share of the pad columns (percent of the 32-row tiles, the last ones) that k_flat_rows stores instead of k_flat_words
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
@@ -125,6 +135,10 @@ struct genztok {
     // pinned host pool
     std::multimap<size_t, void*> host_pool;
     size_t host_pool_bytes = 0;
+    // What a pooled result plane still holds from its last use: the same [rows, width] shape with everything behind column
+    // `dirty_cols` equal to padding.  A call that reuses it copies only the columns that can differ (see encode_fixed_pipelined).
+    struct PlaneMeta { int64_t rows; int32_t width, dirty_cols, elt; int32_t pad; };
+    std::map<void*, PlaneMeta> plane_meta;
 };
 
 namespace {
@@ -257,19 +271,21 @@ int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     const uint64_t B = (uint64_t)h->max_chunk_bytes;
     const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
     CU(d->slots.ensure(slots * sizeof(Slot)));
-    CU(d->key_arena.ensure(B + 64));
+    CU(d->key_arena.ensure(B + B / 3 + 128));                      // (long keys are stored 8-byte aligned: up to 7 bytes of padding for 25 or more)
     CU(d->tok_arena.ensure((2 * B + 64) * 4));
     CU(d->pending.ensure((B / 2 + 64) * 4));
     CU(d->ctr.ensure(C_COUNT * 8));
+    CU(d->rank_scratch.ensure((B + 64) * 4));
     // on the stream that runs the kernels of this call (the handle's own stream is non-blocking: nothing else orders it with the caller's)
     CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), st));
     CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, st));
     WordCache& C = d->C;
     C.slots = d->slots.as<Slot>(); C.mask = (uint32_t)(slots - 1);
-    C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + 64;
+    C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + B / 3 + 64;
     C.tok_arena = d->tok_arena.as<uint32_t>(); C.tok_cap = 2 * B + 64;
     C.pending = d->pending.as<uint32_t>(); C.pending_cap = B / 2 + 64;
     C.ctr = d->ctr.as<unsigned long long>();
+    C.rank_scratch = d->rank_scratch.as<uint32_t>(); C.rank_cap = B + 64;
     d->cache_ready = true;
     return GENZTOK_OK;
 }
@@ -393,7 +409,7 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
                  uint64_t n1 = 0) {
     {
         LaunchScope ls(h, d, "k_cache_guard");
-        CU(launch_pdl(k_cache_guard, dim3(1), dim3(1), 0, st, d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)chunk_bytes, (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force));
+        CU(launch_pdl(k_cache_guard, dim3(1), dim3(1), 0, st, d->C, (unsigned long long)(chunk_bytes / 2 + 2), (unsigned long long)(chunk_bytes + chunk_bytes / 3 + 8), (unsigned long long)(chunk_bytes + chunk_bytes / 2 + 2), force));
     }
     {
         LaunchScope ls(h, d, "k_cache_clear");
@@ -405,7 +421,7 @@ int launch_guard(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_byte
 
 int launch_bpe(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     LaunchScope ls(h, d, "k_bpe_pending");
-    CU(launch_pdl(k_bpe_pending, dim3(d->sm_count * 4), dim3(256), 0, st, d->T, d->C));
+    CU(launch_pdl(k_bpe_pending, dim3(d->sm_count * 6), dim3(256), 0, st, d->T, d->C));      // latency bound (pair-table look-ups): as many warps as fit
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
@@ -688,10 +704,17 @@ void genztok_destroy(genztok_t* h) {
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
                           &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->dec_lead, &d->tok_flag, &d->tok_len, &d->tok_pos, &d->slots,
-                          &d->key_arena, &d->tok_arena, &d->pending, &d->ctr})
+                          &d->key_arena, &d->tok_arena, &d->pending, &d->ctr, &d->rank_scratch})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : d->free_events) cudaEventDestroy(e);
+        for (auto& sg : d->stage) {
+            for (DevBuf* b : {&sg.text, &sg.toff, &sg.pair, &sg.poff, &sg.ids, &sg.mask, &sg.tt, &sg.seq, &sg.row_len, &sg.seq_len, &sg.status, &sg.extent}) b->release();
+            for (cudaEvent_t e : {sg.h2d, sg.k, sg.d2h}) if (e) cudaEventDestroy(e);
+        }
+        if (d->s_in) cudaStreamDestroy(d->s_in);
+        if (d->s_out) cudaStreamDestroy(d->s_out);
+        if (d->h_extent) cudaFreeHost(d->h_extent);
         if (d->last_done) cudaEventDestroy(d->last_done);
         d->synth_len.release();
         for (auto& fb : d->flat) for (DevBuf* b : {&fb.dsb, &fb.st, &fb.tpref, &fb.cnt, &fb.wtok}) b->release();
@@ -774,6 +797,11 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "pad_box_cols") {
         if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "pad_box_cols must be 0 or a multiple of 16 up to 256");
         h->pad_box_cols = value;
+    } else if (n == "no_copy_kernel") {
+        h->no_copy_kernel = value;
+    } else if (n == "copy_blocks") {
+        if (value < 1 || value > 4096) return fail(h, GENZTOK_E_INVALID, "copy_blocks must be in 1..4096");
+        h->copy_blocks = value;
     } else if (n == "l2_policy") {
         h->l2_policy = value;
     } else if (n == "rows_pad_pct") {
@@ -870,7 +898,7 @@ void genztok_free_encoded(genztok_t* h, genztok_encoded_t* out) {
     {
         std::lock_guard<std::mutex> lk(h->mu);
         for (auto& pr : ob->pinned) {
-            if (h->host_pool_bytes + pr.second > (size_t)8 << 30) cudaFreeHost(pr.first);
+            if (h->host_pool_bytes + pr.second > (size_t)8 << 30) { h->plane_meta.erase(pr.first); cudaFreeHost(pr.first); }
             else { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
         }
     }
@@ -891,10 +919,14 @@ struct EncodeJob {
     int32_t max_len; int padding, truncation; uint32_t flags;
     bool has_pair, has_max_len, want_spans, fixed, want_tt, want_seq;
     genztok_encoded_t* out;
+    int32_t old_dirty[4];          // fixed layout: columns of the result planes (ids, mask, token types, sequence ids) that may hold something
+                                   // other than padding from the buffer's last use (the width: unknown / a fresh buffer)
 };
 struct EncodePart {
     int rc = GENZTOK_OK;
     std::string err;
+    int32_t extent = 0;            // fixed layout: columns that can differ from padding, max over this part's chunks
+    int64_t d2h_bytes = 0;
     std::vector<int32_t> ids, spans; std::vector<uint8_t> mask; std::vector<int8_t> tt, seq;
     int64_t total = 0, span_total = 0, tokens = 0;
 };
@@ -933,6 +965,124 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
     CUF(cudaMemcpyAsync(&tokens_before, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaStreamSynchronize(st));
 
+    if (fixed) {
+        // ---- fixed layout, pipelined over chunks: H2D(i + 1) | kernels(i) | D2H(i - 1) on three streams, two sets of chunk buffers.
+        // Only the columns that can differ from padding travel back: [0, max(extent of the chunk, what the pooled host plane still
+        // holds from its last use)), rounded up to 32; a fresh host plane takes whole rows once.
+        const size_t nc = cuts.size() - 1;
+        if (!d->s_in) CUF(cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking));
+        if (!d->s_out) CUF(cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking));
+        if (!d->h_extent) CUF(cudaHostAlloc(reinterpret_cast<void**>(&d->h_extent), 64, cudaHostAllocDefault));
+        int64_t mm = 0, mtb = 0, mpb = 0;
+        for (size_t ci = 0; ci < nc; ci++) {
+            mm = std::max(mm, cuts[ci + 1] - cuts[ci]);
+            mtb = std::max(mtb, J.text_off[cuts[ci + 1]] - J.text_off[cuts[ci]]);
+            if (has_pair) mpb = std::max(mpb, J.pair_off[cuts[ci + 1]] - J.pair_off[cuts[ci]]);
+        }
+        const size_t mtot = (size_t)mm * (size_t)max_len;
+        for (int sidx = 0; sidx < (nc > 1 ? 2 : 1); sidx++) {
+            DeviceCtx::Stage& sg = d->stage[sidx];
+            for (cudaEvent_t* e : {&sg.h2d, &sg.k, &sg.d2h}) if (!*e) CUF(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            CUF(sg.text.ensure((size_t)mtb + 96)); CUF(sg.toff.ensure((size_t)(mm + 1) * 8));
+            if (has_pair) { CUF(sg.pair.ensure((size_t)mpb + 96)); CUF(sg.poff.ensure((size_t)(mm + 1) * 8)); }
+            CUF(sg.ids.ensure(mtot * 4)); CUF(sg.mask.ensure(mtot)); CUF(sg.row_len.ensure((size_t)mm * 4)); CUF(sg.extent.ensure(16));
+            if (want_tt) CUF(sg.tt.ensure(mtot));
+            if (want_seq) CUF(sg.seq.ensure(mtot));
+            if (has_pair) { CUF(sg.seq_len.ensure((size_t)mm * 4)); CUF(sg.status.ensure((size_t)mm)); }
+        }
+        auto issue_h2d = [&](size_t ci) -> bool {
+            DeviceCtx::Stage& sg = d->stage[ci & 1];
+            const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], m = r1 - r0;
+            const int64_t tb0 = J.text_off[r0], tb = J.text_off[r1] - tb0;
+            if (ci >= 2 && cudaStreamWaitEvent(d->s_in, sg.k, 0) != cudaSuccess) return false;      // the kernels of chunk ci - 2 have read this set's inputs
+            // Offsets stay absolute (as in the caller's buffer): the chunk is copied to dev + (tb0 & 15) and the base pointer is
+            // shifted by -tb0, so that base + 16k is 16-byte aligned, as the kernels' 16-byte loads need.
+            if (tb && cudaMemcpyAsync(sg.text.as<uint8_t>() + (tb0 & 15), J.text + tb0, (size_t)tb, cudaMemcpyHostToDevice, d->s_in) != cudaSuccess) return false;
+            if (cudaMemcpyAsync(sg.toff.p, J.text_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, d->s_in) != cudaSuccess) return false;
+            if (has_pair) {
+                const int64_t pb0 = J.pair_off[r0], pb = J.pair_off[r1] - pb0;
+                if (pb && cudaMemcpyAsync(sg.pair.as<uint8_t>() + (pb0 & 15), J.pair + pb0, (size_t)pb, cudaMemcpyHostToDevice, d->s_in) != cudaSuccess) return false;
+                if (cudaMemcpyAsync(sg.poff.p, J.pair_off + r0, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, d->s_in) != cudaSuccess) return false;
+            }
+            return cudaEventRecord(sg.h2d, d->s_in) == cudaSuccess;
+        };
+        auto fail_sync = [&]() { cudaStreamSynchronize(d->s_in); cudaStreamSynchronize(st); cudaStreamSynchronize(d->s_out); };
+        if (nc && !issue_h2d(0)) { fail_sync(); PFAIL(GENZTOK_E_CUDA, "host to device copy failed: %s", cudaGetErrorString(cudaGetLastError())) }
+        for (size_t ci = 0; ci < nc; ci++) {
+            DeviceCtx::Stage& sg = d->stage[ci & 1];
+            const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], m = r1 - r0;
+            const int64_t tb0 = J.text_off[r0], tb = J.text_off[r1] - tb0;
+            const int64_t pb0 = has_pair ? J.pair_off[r0] : 0, pb = has_pair ? J.pair_off[r1] - pb0 : 0;
+            // kernels of chunk ci: behind its inputs, and behind the copy-out of the chunk that used this set of planes before
+            CUF(cudaStreamWaitEvent(st, sg.h2d, 0));
+            if (ci >= 2) CUF(cudaStreamWaitEvent(st, sg.d2h, 0));
+            Side a{sg.text.as<uint8_t>() + (tb0 & 15) - tb0, sg.toff.as<int64_t>(), tb};
+            Side b{has_pair ? sg.pair.as<uint8_t>() + (pb0 & 15) - pb0 : nullptr, sg.poff.as<int64_t>(), pb};
+            genztok_dev_planes_t P{};
+            P.input_ids = sg.ids.as<int32_t>(); P.attention_mask = sg.mask.as<uint8_t>(); P.row_len = sg.row_len.as<int32_t>();
+            if (want_tt) P.token_type_ids = sg.tt.as<int8_t>();
+            if (want_seq) P.sequence_id = sg.seq.as<int8_t>();
+            if (has_pair) { P.seq_len = sg.seq_len.as<int32_t>(); P.row_status = sg.status.as<uint8_t>(); }
+            { int _rc = encode_fixed_on_device(h, d, st, a, has_pair ? &b : nullptr, m, max_len, J.flags, P);
+              if (_rc) { part->rc = _rc; { std::lock_guard<std::mutex> _l(h->err_mu); part->err = h->err; } fail_sync(); return; } }
+            CUF(cudaMemsetAsync(sg.extent.p, 0, 4, st));
+            { LaunchScope ls(h, d, "k_row_extent");
+              k_row_extent<<<(unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)d->sm_count * 4), 256, 0, st>>>(P.row_len, has_pair ? P.seq_len : nullptr, m, sg.extent.as<int32_t>()); }
+            CUF(cudaMemcpyAsync(d->h_extent + (ci & 1), sg.extent.p, 4, cudaMemcpyDeviceToHost, st));
+            CUF(cudaEventRecord(sg.k, st));
+            // the next chunk's inputs travel while these kernels run
+            if (ci + 1 < nc && !issue_h2d(ci + 1)) { fail_sync(); PFAIL(GENZTOK_E_CUDA, "host to device copy failed: %s", cudaGetErrorString(cudaGetLastError())) }
+            // copy-out of chunk ci: the host learns the extent (the only wait of this loop), then the trimmed planes go on their own stream
+            CUF(cudaEventSynchronize(sg.k));
+            const int32_t kc = std::min<int32_t>(max_len, std::max<int32_t>(d->h_extent[ci & 1], 1));
+            part->extent = std::max(part->extent, kc);
+            CUF(cudaStreamWaitEvent(d->s_out, sg.k, 0));
+            const size_t o0 = (size_t)r0 * (size_t)max_len;
+            CopyOutArgs CO{};
+            CO.m = m;
+            auto copy_plane = [&](void* host, const void* dev, size_t elt, int32_t old_dirty) -> cudaError_t {
+                const int32_t cols = std::min<int32_t>(max_len, (std::max(kc, old_dirty) + 31) & ~31);
+                part->d2h_bytes += (int64_t)m * cols * (int64_t)elt;
+                uint8_t* dst = reinterpret_cast<uint8_t*>(host) + o0 * elt;
+                if (cols >= max_len) return cudaMemcpyAsync(dst, dev, (size_t)m * (size_t)max_len * elt, cudaMemcpyDeviceToHost, d->s_out);
+                void* dmap = nullptr;                                     // trimmed rows: stores of a kernel into the mapped host plane
+                if (!h->no_copy_kernel && ((size_t)max_len * elt) % 16 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                    cudaHostGetDevicePointer(&dmap, dst, 0) == cudaSuccess && dmap) {
+                    CO.p[CO.n_planes++] = CopyOutPlane{reinterpret_cast<const uint8_t*>(dev), reinterpret_cast<uint8_t*>(dmap), (uint32_t)(max_len * elt), (uint32_t)(cols * elt)};
+                    return cudaSuccess;
+                }
+                cudaGetLastError();
+                return cudaMemcpy2DAsync(dst, (size_t)max_len * elt, dev, (size_t)max_len * elt, (size_t)cols * elt, (size_t)m, cudaMemcpyDeviceToHost, d->s_out);
+            };
+            CUF(copy_plane(out->input_ids, sg.ids.p, 4, J.old_dirty[0]));
+            CUF(copy_plane(out->attention_mask, sg.mask.p, 1, J.old_dirty[1]));
+            if (want_tt) CUF(copy_plane(out->token_type_ids, sg.tt.p, 1, J.old_dirty[2]));
+            if (want_seq) CUF(copy_plane(out->sequence_id, sg.seq.p, 1, J.old_dirty[3]));
+            if (CO.n_planes) {
+                LaunchScope::cur_stream = d->s_out;
+                { LaunchScope ls(h, d, "k_copy_out"); k_copy_out<<<(unsigned)std::max<int64_t>(1, h->copy_blocks), 256, 0, d->s_out>>>(CO); }
+                LaunchScope::cur_stream = st;
+                CUF(cudaGetLastError());
+            }
+            CUF(cudaMemcpyAsync(out->row_len + r0, sg.row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, d->s_out));
+            part->d2h_bytes += m * 4;
+            if (has_pair) {
+                CUF(cudaMemcpyAsync(out->seq_len + r0, sg.seq_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, d->s_out));
+                CUF(cudaMemcpyAsync(out->row_status + r0, sg.status.p, (size_t)m, cudaMemcpyDeviceToHost, d->s_out));
+                part->d2h_bytes += m * 5;
+            }
+            CUF(cudaEventRecord(sg.d2h, d->s_out));
+        }
+        CUF(cudaStreamSynchronize(d->s_out));
+        unsigned long long tokens_after = 0, nerr = 0;
+        CUF(cudaMemcpyAsync(&tokens_after, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
+        CUF(cudaMemcpyAsync(&nerr, d->C.ctr + C_ERR, 8, cudaMemcpyDeviceToHost, st));
+        CUF(cudaStreamSynchronize(st));
+        if (nerr) PFAIL(GENZTOK_E_CUDA, "internal error: device pipeline reported %llu inconsistencies", nerr)
+        part->tokens = (int64_t)(tokens_after - tokens_before);
+        return;
+    }
+
     for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
         const int64_t r0 = cuts[ci], r1 = cuts[ci + 1], m = r1 - r0;
         const int64_t tb0 = J.text_off[r0], tb = J.text_off[r1] - tb0;
@@ -950,29 +1100,6 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         }
         Side a{d->text.as<uint8_t>() + ta - tb0, d->toff.as<int64_t>(), tb};
         Side b{has_pair ? d->pair.as<uint8_t>() + pa - pb0 : nullptr, d->poff.as<int64_t>(), pb};
-
-        if (fixed) {
-            const size_t tot = (size_t)m * (size_t)max_len;
-            CUF(d->ids.ensure(tot * 4)); CUF(d->mask.ensure(tot)); CUF(d->row_len.ensure((size_t)m * 4));
-            genztok_dev_planes_t P{};
-            P.input_ids = d->ids.as<int32_t>(); P.attention_mask = d->mask.as<uint8_t>(); P.row_len = d->row_len.as<int32_t>();
-            if (want_tt) { CUF(d->tt.ensure(tot)); P.token_type_ids = d->tt.as<int8_t>(); }
-            if (want_seq) { CUF(d->seq.ensure(tot)); P.sequence_id = d->seq.as<int8_t>(); }
-            if (has_pair) { CUF(d->seq_len.ensure((size_t)m * 4)); CUF(d->status.ensure((size_t)m)); P.seq_len = d->seq_len.as<int32_t>(); P.row_status = d->status.as<uint8_t>(); }
-            FAIL_RC(encode_fixed_on_device(h, d, st, a, has_pair ? &b : nullptr, m, max_len, J.flags, P));
-            const size_t o0 = (size_t)r0 * (size_t)max_len;
-            CUF(cudaMemcpyAsync(out->input_ids + o0, d->ids.p, tot * 4, cudaMemcpyDeviceToHost, st));
-            CUF(cudaMemcpyAsync(out->attention_mask + o0, d->mask.p, tot, cudaMemcpyDeviceToHost, st));
-            CUF(cudaMemcpyAsync(out->row_len + r0, d->row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            if (want_tt) CUF(cudaMemcpyAsync(out->token_type_ids + o0, d->tt.p, tot, cudaMemcpyDeviceToHost, st));
-            if (want_seq) CUF(cudaMemcpyAsync(out->sequence_id + o0, d->seq.p, tot, cudaMemcpyDeviceToHost, st));
-            if (has_pair) {
-                CUF(cudaMemcpyAsync(out->seq_len + r0, d->seq_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-                CUF(cudaMemcpyAsync(out->row_status + r0, d->status.p, (size_t)m, cudaMemcpyDeviceToHost, st));
-            }
-            CUF(cudaStreamSynchronize(st));   // device buffers are reused by the next chunk
-            continue;
-        }
 
         // ---- ragged layout ---------------------------------------------------------------------------
         if (tb + pb + 16 > h->max_chunk_bytes) PFAIL(GENZTOK_E_LIMIT, "chunk too large")
@@ -1090,7 +1217,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
     out->_owner = ob;
     out->n = n; out->has_pair = has_pair;
     auto free_nolock = [&]() {
-        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        for (auto& pr : ob->pinned) { h->plane_meta.erase(pr.first); h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
         for (void* p : ob->mallocs) free(p);
         delete ob;
         memset(out, 0, sizeof *out);
@@ -1118,6 +1245,15 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         out->row_off[0] = 0;
     }
 #undef OOM_CHECK
+    // what the pooled planes still hold from their last use (see encode_rows_on_device, fixed layout)
+    void* const planes4[4] = {out->input_ids, out->attention_mask, out->token_type_ids, out->sequence_id};
+    const int32_t elts4[4] = {4, 1, 1, 1};
+    for (int k = 0; k < 4; k++) {
+        J.old_dirty[k] = max_len;
+        if (!fixed || !planes4[k]) continue;
+        auto it = h->plane_meta.find(planes4[k]);
+        if (it != h->plane_meta.end() && it->second.rows == n && it->second.width == max_len && it->second.elt == elts4[k]) J.old_dirty[k] = it->second.dirty_cols;
+    }
 
     // Shard by document across the handle's devices: contiguous row ranges balanced by bytes, one host
     // thread per device, no collective; every device writes its own rows of the result.
@@ -1147,8 +1283,13 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
     for (auto& pt : parts)
         if (pt.rc) { free_nolock(); { std::lock_guard<std::mutex> l(h->err_mu); h->err = pt.err; } return pt.rc; }
     out->real_tokens = 0;
-    for (auto& pt : parts) out->real_tokens += pt.tokens;
+    out->d2h_bytes = 0;
+    for (auto& pt : parts) { out->real_tokens += pt.tokens; out->d2h_bytes += pt.d2h_bytes; }
     if (fixed) {
+        int32_t extent = 1;
+        for (auto& pt : parts) extent = std::max(extent, pt.extent);
+        for (int k = 0; k < 4; k++)
+            if (planes4[k]) h->plane_meta[planes4[k]] = genztok::PlaneMeta{n, max_len, std::min<int32_t>(max_len, (extent + 31) & ~31), elts4[k], 0};
         if (J.want_tt) for (int64_t r = 0; r < n; r++) out->tt_len[r] = max_len;
     } else {
         // stitch the parts: shift every part's row offsets by what came before it, concatenate the flat planes

@@ -687,6 +687,37 @@ __global__ void k_mask_flat(const int32_t* ids, int64_t n, int32_t pad, uint8_t*
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = ids[i] != pad;
 }
 
+// Columns of a fixed-layout chunk that can differ from padding: max over rows of the row length and, for pairs, of the
+// sequence-id length (token types run that far).  The host copies only those columns back (genztok.cu, encode_fixed_pipelined).
+__global__ void __launch_bounds__(256) k_row_extent(const int32_t* row_len, const int32_t* seq_len, int64_t n, int32_t* out) {
+    int32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        m = max(m, row_len[i]);
+        if (seq_len) m = max(m, seq_len[i]);
+    }
+    m = __reduce_max_sync(FULL_MASK, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// The first `wbytes` bytes (a multiple of 16) of every row of up to four [m, pitch] planes from device memory to mapped pinned
+// host memory, 16 bytes a thread: the copy engine moves such 128-byte rows at a third of the link's rate, coalesced stores of an
+// SM reach it.  (Runs on the copy-out stream beside the next chunk's kernels; a few blocks keep PCIe busy.)
+struct CopyOutPlane { const uint8_t* src; uint8_t* dst; uint32_t pitch, wbytes; };
+struct CopyOutArgs { CopyOutPlane p[4]; int32_t n_planes; int64_t m; };
+__global__ void __launch_bounds__(256) k_copy_out(CopyOutArgs A) {
+    for (int k = 0; k < A.n_planes; k++) {
+        const CopyOutPlane P = A.p[k];
+        const uint32_t upr = P.wbytes >> 4;                                   // 16-byte units per row
+        const int64_t total = A.m * (int64_t)upr;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = t / upr;
+            const uint32_t u = (uint32_t)(t - r * upr);
+            const size_t o = (size_t)r * P.pitch + (size_t)u * 16;
+            *reinterpret_cast<uint4*>(P.dst + o) = __ldcs(reinterpret_cast<const uint4*>(P.src + o));
+        }
+    }
+}
+
 // ---- word cache housekeeping -------------------------------------------------------------------------
 // Decide whether the cache can take the worst case of the next chunk; if not, schedule a reset.
 __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsigned long long need_keys, unsigned long long need_toks, int force) {
@@ -696,7 +727,7 @@ __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsign
     const bool reset = force || (c[C_SLOTS] + need_slots) * 2 > cap || c[C_KEYS] + need_keys > C.key_cap || c[C_TOKS] + need_toks > C.tok_cap;
     c[C_RESET] = reset;
     if (reset) { c[C_SLOTS] = 0; c[C_KEYS] = 0; c[C_TOKS] = 0; }
-    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0;
+    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0; c[C_SCRATCH] = 0; c[C_TICKET] = 0;
 }
 // ... and two optional word arrays to zero on the way (the document-start bitmaps of the byte-parallel pipeline)
 __global__ void k_cache_clear(WordCache C, uint32_t* z0, uint64_t n0, uint32_t* z1, uint64_t n1) {
@@ -710,6 +741,6 @@ __global__ void k_cache_clear(WordCache C, uint32_t* z0, uint64_t n0, uint32_t* 
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint64_t i = tid; i < n; i += nth) p[i] = z;
 }
-__global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; C.ctr[C_FLATFIX_A] = 0; C.ctr[C_FLATFIX_B] = 0; }
+__global__ void k_reset_lists(WordCache C) { C.ctr[C_PENDING] = 0; C.ctr[C_REDO] = 0; C.ctr[C_FIX] = 0; C.ctr[C_FLATFIX_A] = 0; C.ctr[C_FLATFIX_B] = 0; C.ctr[C_TICKET] = 0; }
 
 }  // namespace gzt

@@ -390,6 +390,7 @@ class Tokenize(object):
         r["attention_mask"] = r._mask.reshape(shape)
         r["row_len"] = r._row_len
         r["real_tokens"] = int(enc.real_tokens)
+        r.d2h_bytes = int(enc.d2h_bytes)
         if r._row_off is not None:
             r["row_off"] = r._row_off
         if r._has_pair:

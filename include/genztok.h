@@ -74,6 +74,8 @@ typedef struct genztok_encoded {
     int32_t *spans;          /* [span_off[n]][2] (first,last) token index pairs, or NULL */
     int64_t real_tokens;     /* sum over rows of attention_mask */
     void *_owner;            /* internal */
+    int64_t d2h_bytes;       /* bytes this call copied from the device to the host (fixed layout: only the columns that can differ
+                              * from padding travel; a recycled result buffer already holds the padding) */
 } genztok_encoded_t;
 
 typedef struct genztok_text {

@@ -730,3 +730,24 @@ def test_token_type_padding_is_the_pad_id(oracle):
         for W in (48, 64):
             be = t.encode_batch(ta, tb, max_len=W)
             assert_matches_oracle(be, o.encode_batch(ta, tb, max_len=W, threads=8), pad_id=blk["pad_id"], what="pad token %r W=%d" % (blk["pad_token"], W))
+
+
+def test_recycled_result_planes_hold_no_stale_columns(tok, oracle):
+    """The host path copies back only the columns that can differ from padding and relies on a recycled result buffer for the
+    rest (genztok.cu, fixed layout): batches of the same shape with long rows first, then short rows, then long ones again, in
+    several chunks, every plane against the oracle each time."""
+    from genz_tokenize_b200 import workload
+    n, W = 5000, 96
+    tok.set_option("chunk_rows", 1536)                                     # four chunks: the two sets of chunk buffers alternate
+    try:
+        for k, (lo, hi, noise) in enumerate([(20, 60, 0.02), (1, 4, 0.0), (3, 13, 0.05), (0, 2, 0.0), (30, 40, 0.0)]):
+            ta, tb = workload.generate_hashed(77 + k, 0, n, 0, lo, hi, noise), workload.generate_hashed(77 + k, 0, n, 1, lo, hi, noise)
+            be = tok.encode_batch(ta, tb, max_len=W)
+            assert_matches_oracle(be, oracle.encode_batch(ta, tb, max_len=W, threads=8), what="recycled planes, batch %d" % k)
+            assert be.d2h_bytes > 0
+            del be
+        ta = workload.generate_hashed(5, 0, n, 0, 1, 3, 0.0)                # single sentences in a buffer that held pairs of the same size
+        be = tok.encode_batch(ta, max_len=W)
+        assert_matches_oracle(be, oracle.encode_batch(ta, None, max_len=W, threads=8), what="recycled planes, singles")
+    finally:
+        tok.set_option("chunk_rows", 1 << 18)
