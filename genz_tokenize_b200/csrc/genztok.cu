@@ -73,6 +73,8 @@ struct DeviceCtx {
     DevBuf L, keep, out_len, row_off, tail, redo, fix, misc, nwA, nwB, span_cnt, span_off, spans, scan_tmp, prep_out;
     DevBuf slots, key_arena, tok_arena, pending, ctr, rank_scratch;
     DevBuf dec_lead;                              // decode: per-row description left by the length pass for the write pass
+    DevBuf dec_stat;                              // decode, fixed-width rows: ids in front of the pad runs, summed by the length pass
+    double dec_avg_lead = -1;                     // ... per row, once the host has read it (-1: not known for the current batch)
     DevBuf tok_flag, tok_len, tok_pos;            // decode of ragged rows by id: last-of-row flags, bytes per id, their scan
     int64_t tok_base = 0, tok_n = -1;             // the ids that scan describes
     struct { const void *ids = nullptr, *ids_off = nullptr, *out_off = nullptr; int64_t n = -1; int32_t width = 0; int by_id = 0; } dec_sig;   // the batch it describes
@@ -119,6 +121,7 @@ struct genztok {
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
+    int64_t decode_write = 0;            // fixed-width decode, write pass: 0 = by the average lead, 1 = warp per row, 2 = lane per row (test knob)
     int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
     int64_t copy_blocks = 64;            // blocks of k_copy_out
     int64_t l2_policy = 0;               // bit 0: text read evict-first, bit 1: word arrays stored evict-last (k_flat_words; experiments)
@@ -704,7 +707,7 @@ void genztok_destroy(genztok_t* h) {
         for (void* p : d->table_allocs) cudaFree(p);
         for (DevBuf* b : {&d->text, &d->toff, &d->pair, &d->poff, &d->ids, &d->mask, &d->tt, &d->seq, &d->row_len, &d->seq_len, &d->tt_len,
                           &d->status, &d->L, &d->keep, &d->out_len, &d->row_off, &d->tail, &d->redo, &d->fix, &d->misc, &d->nwA, &d->nwB, &d->span_cnt, &d->span_off, &d->spans, &d->scan_tmp, &d->prep_out, &d->dec_lead, &d->tok_flag, &d->tok_len, &d->tok_pos, &d->slots,
-                          &d->key_arena, &d->tok_arena, &d->pending, &d->ctr, &d->rank_scratch})
+                          &d->key_arena, &d->tok_arena, &d->pending, &d->ctr, &d->rank_scratch, &d->dec_stat})
             b->release();
         for (auto& e : d->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         for (auto e : d->free_events) cudaEventDestroy(e);
@@ -797,6 +800,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     } else if (n == "pad_box_cols") {
         if (value < 0 || value > 256 || (value & 15)) return fail(h, GENZTOK_E_INVALID, "pad_box_cols must be 0 or a multiple of 16 up to 256");
         h->pad_box_cols = value;
+    } else if (n == "decode_write") {
+        h->decode_write = value;
     } else if (n == "no_copy_kernel") {
         h->no_copy_kernel = value;
     } else if (n == "copy_blocks") {
@@ -1405,6 +1410,12 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
     auto length_pass = [&]() -> int {
         CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
         A.out_len = d->out_len.as<int64_t>();
+        d->dec_avg_lead = -1;
+        if (fixed) {
+            CU(d->dec_stat.ensure(16));
+            CU(cudaMemsetAsync(d->dec_stat.p, 0, 8, st));
+            A.lead_sum = d->dec_stat.as<unsigned long long>();
+        }
         if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_len_fixed"); k_decode_len_fixed<<<grid_len, 256, 0, st>>>(d->T, A); }
         else if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode_len<<<grid_len, 256, 0, st>>>(d->T, A); }
         d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width; d->dec_sig.by_id = 0;
@@ -1414,14 +1425,32 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
         { int rc = length_pass(); if (rc) return rc; }
         { int rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d_out_off, n); if (rc) return rc; }
         if (total_bytes) {
+            unsigned long long lead_sum = 0;
             CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+            if (fixed) CU(cudaMemcpyAsync(&lead_sum, d->dec_stat.p, 8, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            if (fixed && n > 0) d->dec_avg_lead = (double)lead_sum / (double)n;
         }
         return GENZTOK_OK;
     }
     // the write pass reads what the length pass of the same batch left in dec_lead; after another batch's length pass it is redone
     if (!same_batch(0)) { int rc = length_pass(); if (rc) return rc; }
-    if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_write_fixed"); k_decode_write_fixed<<<grid_write, 256, 0, st>>>(d->T, A); }
+    // Two write kernels for fixed-width rows: a lane per row assembles short leads (single sentences, ~10 pieces in front of the
+    // pad run); the whole warp gathers long ones 32 pieces at a time (sentence pairs, ~20).  The length pass counted the pieces.
+    const bool by_lanes = h->decode_write == 2 || (h->decode_write == 0 && d->dec_avg_lead >= 0 && d->dec_avg_lead <= 14.0);
+    if (n > 0 && fixed && !by_lanes) {
+        LaunchScope ls(h, d, "k_decode_write_fixed");
+        k_decode_write_fixed_coop<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * 5)), 256, 0, st>>>(d->T, A);
+    } else if (n > 0 && fixed) {
+        const size_t smem = 8 * (32 * (size_t)DWF_STRIDE + 16);
+        static bool attr_set = false;
+        if (!attr_set) { CU(cudaFuncSetAttribute(k_decode_write_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode_write_fixed, 256, smem));
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * std::max(occ, 1)));
+        LaunchScope ls(h, d, "k_decode_write_fixed");
+        k_decode_write_fixed<<<grid, 256, smem, st>>>(d->T, A);
+    }
     else if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode_write<<<grid_write, 256, 0, st>>>(d->T, A); }
     CU(cudaGetLastError());
     return GENZTOK_OK;

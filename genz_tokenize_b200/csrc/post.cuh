@@ -228,6 +228,7 @@ struct DecArgs {
     const int64_t* out_off;   // per row start (pass 2)
     uint8_t* out;
     DecLead* lead;            // written by pass 1, read by pass 2
+    unsigned long long* lead_sum;   // fixed-width pass 1: ids in front of the pad runs, summed (NULL: not wanted)
 };
 
 __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool last, uint32_t* off, uint32_t* len) {
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArg
     const int nseg = (W + 127) >> 7;
     const int own_lane = (lim & 127) >> 2;                           // the lane whose last vector ends with the row's last id
     const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
+    uint32_t lead_ids = 0;
     for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
         const int64_t r0 = (int64_t)tile * 32;
         const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
@@ -416,8 +418,12 @@ __global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArg
             }
             if (A.lead) *reinterpret_cast<uint4*>(A.lead + r0 + lane) = d;
             A.out_len[r0 + lane] = run;
+            lead_ids += (int32_t)d.x >= 0 ? d.x : (uint32_t)W;
         }
     }
+    // ids in front of the pad runs, summed over the batch: the host picks the write kernel by their average
+    lead_ids = __reduce_add_sync(FULL_MASK, lead_ids);
+    if (lane == 0 && A.lead_sum && lead_ids) atomicAdd(A.lead_sum, (unsigned long long)lead_ids);
 }
 #undef DEC_MID
 
@@ -589,9 +595,10 @@ __global__ void __launch_bounds__(256, 4) k_decode_write(DevTables T, DecArgs A)
     }
 }
 
-// Pass 2 for fixed-width rows: a warp takes 32 consecutive rows, lane j reads row j's offset and description (coalesced, once
+// Pass 2 for fixed-width rows with long leads (sentence pairs: ~20 pieces in front of the pad run): the pieces of a row are
+// gathered by the whole warp, 32 at a time (dec_write_row).  A warp takes 32 consecutive rows, lane j reads row j's offset and description (coalesced, once
 // per 32 rows) and hands them out by shuffle; the first ids of the next row are loaded before this row is written.
-__global__ void __launch_bounds__(256, 5) k_decode_write_fixed(DevTables T, DecArgs A) {
+__global__ void __launch_bounds__(256, 5) k_decode_write_fixed_coop(DevTables T, DecArgs A) {
     __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
     __shared__ __align__(16) uint8_t padtab[8][8][16];
     const DecWarp w = dec_warp_setup(T, stage, padtab);
@@ -626,6 +633,129 @@ __global__ void __launch_bounds__(256, 5) k_decode_write_fixed(DevTables T, DecA
             }
             dec_write_row(T, A.out, ids, W, g0, ld, id_first, w);
         }
+    }
+}
+
+// Pass 2 for fixed-width rows with short leads (single sentences: ~10 pieces).  A warp takes 32 consecutive rows.
+//  A. A LANE PER ROW assembles the text of the ids in front of the row's trailing pad run (the "lead": ~20 pieces, ~130 bytes
+//     for a sentence pair) in shared memory -- piece after piece, eight bytes a store round, at the row's alignment in the
+//     output (g0 & 15), and fills it up to the next 16-byte boundary with the beginning of the pad run's periodic text.
+//  B. The WARP then writes each row with aligned 16-byte stores, a lane per unit: the lead units from shared memory, the run's
+//     units from the table of the periodic text by phase; the row's first partial unit (shared with the row before) and its
+//     tail (rest of the run + the last piece) go bytewise.
+//  Rows without a usable pad run, with a long lead or a very long vocabulary entry take the general row routine afterwards.
+// 330 -> ~100 warp instructions per row: the write pass was bound by instruction issue, not by memory.
+static const int DWF_STRIDE = 256;      // bytes of shared memory per row (a multiple of 16: the units are read back as 16-byte vectors)
+static const int DWF_LEADMAX = 184;     // longest lead (bytes) assembled there: 15 (alignment) + lead + 15 (fill) + 15 + 24 (tail) <= 256
+static const int DWF_LASTMAX = 24;      // longest last piece on the fast path
+struct __align__(16) DwfRow { long long g0; uint16_t nrun; uint8_t nl, q0, tail, fast; uint16_t s_bytes; };
+__global__ void __launch_bounds__(256, 3) k_decode_write_fixed(DevTables T, DecArgs A) {
+    extern __shared__ __align__(16) uint8_t dwf_smem[];
+    __shared__ __align__(16) uint8_t padtab[8][8][16];
+    __shared__ DwfRow rowinfo[8][32];
+    const int wib = threadIdx.x >> 5;
+    uint8_t* const leadbuf = dwf_smem + (size_t)wib * (32 * DWF_STRIDE + 16);            // [32][DWF_STRIDE]; the general routine's staging buffer aliases it
+    const DecWarp w = dec_warp_setup(T, reinterpret_cast<uint8_t (*)[DEC_CAP + 16]>(dwf_smem), padtab);
+    DecWarp wg = w;
+    wg.ob = leadbuf;
+    const int lane = w.lane;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const bool use_lead = A.lead != nullptr && w.padL != 0;
+    const int W = A.width;
+    const uint32_t L = w.padL, nid = (uint32_t)T.n_ids;
+    const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
+    for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
+        const int64_t r0 = (int64_t)tile * 32;
+        const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
+        // ---- A. my row (a lane per row): its lead, the fill up to the next unit and its tail into shared memory
+        {
+            DwfRow me; me.g0 = 0; me.nrun = 0; me.nl = 0; me.q0 = 0; me.tail = 0; me.fast = 0; me.s_bytes = 0;
+            uint4 ld = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+            if (lane < rows) {
+                me.g0 = A.out_off[r0 + lane];
+                if (use_lead) ld = *reinterpret_cast<const uint4*>(A.lead + r0 + lane);
+                const int32_t n_lead = (int32_t)ld.x;
+                const uint32_t run_total = n_lead >= 0 ? (uint32_t)(W - 1 - n_lead) * L : 0u;
+                bool fast = n_lead >= 0 && ld.y <= (uint32_t)DWF_LEADMAX && run_total >= 32u && ld.w <= (uint32_t)DWF_LASTMAX;
+                if (fast) {
+                    const int32_t* rid = A.ids + (r0 + lane) * (int64_t)W;
+                    uint8_t* sb = leadbuf + lane * DWF_STRIDE;
+                    const uint32_t a = (uint32_t)(me.g0 & 15);
+                    uint32_t pos = a;
+                    for (int32_t i0 = 0; i0 < n_lead && fast; i0 += 4) {
+                        const int4 v4 = *reinterpret_cast<const int4*>(rid + i0);        // (W is a multiple of 4 and the rows are 16-byte aligned)
+                        const int32_t idv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            if (i0 + t < n_lead && fast) {
+                                const uint32_t k = min((uint32_t)idv[t], nid);                   // decoder.get(i, unk_token)
+                                const uint32_t dsc = T.mid_desc[k];
+                                const uint32_t len = dsc & 255u;
+                                if (len == 255u || pos + len > 15u + (uint32_t)DWF_LEADMAX) { fast = false; break; }
+                                const uint8_t* src = T.form_blob + (dsc >> 8) * 8u;
+                                for (uint32_t b = 0; b < len; b += 8) {
+                                    // eight bytes a round; what lands behind the piece's end is overwritten by the next piece (or the fill)
+                                    const uint64_t v = *reinterpret_cast<const uint64_t*>(src + b);
+                                    uint8_t* dk = sb + pos + b;
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) dk[q] = (uint8_t)(v >> (8 * q));
+                                }
+                                pos += len;
+                            }
+                        }
+                    }
+                    if (fast && pos != a + ld.y) fast = false;                          // (cannot happen: pass 1 summed the same lengths)
+                    if (fast) {
+                        uint32_t t = 0;
+                        for (; pos & 15u; t++, pos++) sb[pos] = (uint8_t)(w.padP >> (8 * dec_mod(t, L, w.padM)));   // the run's first bytes
+                        const uint32_t nrun = (run_total - t) >> 4, done = t + (nrun << 4), rt = run_total - done;   // whole units of the run; rt < 16 bytes left
+                        for (uint32_t k = 0; k < rt; k++) sb[pos + k] = (uint8_t)(w.padP >> (8 * dec_mod(done + k, L, w.padM)));
+                        const uint8_t* lsrc = T.form_blob + ld.z;                        // the last piece behind the run
+                        for (uint32_t k = 0; k < ld.w; k++) sb[pos + rt + k] = lsrc[k];
+                        me.nl = (uint8_t)(pos >> 4); me.q0 = (uint8_t)t; me.nrun = (uint16_t)min(nrun, 65535u); me.tail = (uint8_t)(rt + ld.w); me.s_bytes = (uint16_t)pos;
+                        if (nrun > 65535u) fast = false;
+                    }
+                }
+                me.fast = fast ? 1 : 0;
+            }
+            rowinfo[wib][lane] = me;
+        }
+        __syncwarp();
+        // ---- B. the rows, one after the other, a lane per 16-byte unit
+        uint32_t slow_rows = 0;
+        for (int j = 0; j < rows; j++) {
+            const DwfRow ri = rowinfo[wib][j];
+            if (!ri.fast) { slow_rows |= 1u << j; continue; }
+            const uint8_t* sb = leadbuf + j * DWF_STRIDE;
+            const uint32_t a = (uint32_t)(ri.g0 & 15);
+            uint8_t* const u0 = A.out + (ri.g0 - a);                                    // the first unit the row touches
+            if ((uint32_t)lane < ri.nl && (lane || !a)) __stcs(reinterpret_cast<uint4*>(u0) + lane, *reinterpret_cast<const uint4*>(sb + 16 * lane));
+            if (a && (uint32_t)lane >= a && lane < 16) u0[lane] = sb[lane];             // the unit shared with the row before: my bytes only
+            uint4* ur = reinterpret_cast<uint4*>(u0) + ri.nl;                           // the run's whole units
+            uint32_t ph = dec_mod((uint32_t)ri.q0 + 16u * (uint32_t)lane, L, w.padM);
+#pragma unroll 1
+            for (uint32_t u = (uint32_t)lane; u < ri.nrun; u += 32) {
+                __stcs(ur + u, *reinterpret_cast<const uint4*>(w.padtab + 16 * ph));
+                ph += w.step; if (ph >= L) ph -= L;
+            }
+            uint8_t* tp = reinterpret_cast<uint8_t*>(ur + ri.nrun);                     // the tail: rest of the run + the last piece
+            for (uint32_t k = (uint32_t)lane; k < ri.tail; k += 32) tp[k] = sb[ri.s_bytes + k];
+        }
+        __syncwarp();
+        // ---- the other rows: the general routine (its staging buffer is the lead buffer, free by now)
+        while (slow_rows) {
+            const int j = __ffs(slow_rows) - 1;
+            slow_rows &= slow_rows - 1;
+            const long long g0 = rowinfo[wib][j].g0;
+            const uint4 ld = use_lead ? *reinterpret_cast<const uint4*>(A.lead + r0 + j) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+            const int32_t* ids = A.ids + (r0 + j) * (int64_t)W;
+            const int ne = (int32_t)ld.x >= 0 ? (int32_t)ld.x : W;
+            const int32_t id_first = lane < ne ? ids[lane] : 0;
+            __syncwarp();
+            dec_write_row(T, A.out, ids, W, g0, ld, id_first, wg);
+            __syncwarp();
+        }
+        __syncwarp();
     }
 }
 

@@ -42,20 +42,49 @@ def bundled_paths():
     if _cache is not None and all(os.path.exists(p) for p in _cache):
         return _cache
     files = _read_pack()
-    for root in (os.path.join(_HERE, "_unpacked"), os.path.join(tempfile.gettempdir(), "genztok_b200_data_%d" % os.getuid())):
+
+    def intact(p, raw):
+        """An unpacked file is trusted only when its bytes are the pack's (a same-size file somebody else put there is not)."""
         try:
-            os.makedirs(root, exist_ok=True)
-            paths = []
-            for name in ("vocab.txt", "bpe.codes"):
-                p = os.path.join(root, name)
-                if not (os.path.exists(p) and os.path.getsize(p) == len(files[name])):
-                    tmp = "%s.%d.tmp" % (p, os.getpid())
-                    with open(tmp, "wb") as f:
-                        f.write(files[name])
-                    os.replace(tmp, p)
-                paths.append(p)
-            _cache = tuple(paths)
-            return _cache
+            with open(p, "rb") as f:
+                return f.read() == raw
         except OSError:
-            continue
+            return False
+
+    def unpack_into(root):
+        paths = []
+        for name in ("vocab.txt", "bpe.codes"):
+            p = os.path.join(root, name)
+            if not intact(p, files[name]):
+                tmp = "%s.%d.tmp" % (p, os.getpid())
+                with open(tmp, "wb") as f:
+                    f.write(files[name])
+                os.replace(tmp, p)
+            paths.append(p)
+        return tuple(paths)
+
+    try:                                                       # beside the package (the usual case: an in-tree or user-owned install)
+        root = os.path.join(_HERE, "_unpacked")
+        os.makedirs(root, exist_ok=True)
+        _cache = unpack_into(root)
+        return _cache
+    except OSError:
+        pass
+    # read-only package: a private directory under the temp dir -- created by this user with mode 0700, or a fresh one
+    # (a predictable name that another user of a shared host could have prepared is not used)
+    root = os.path.join(tempfile.gettempdir(), "genztok_b200_data_%d" % os.getuid())
+    try:
+        os.mkdir(root, 0o700)
+    except FileExistsError:
+        st = os.lstat(root)
+        import stat
+        if not stat.S_ISDIR(st.st_mode) or st.st_uid != os.getuid() or (st.st_mode & 0o077):
+            root = tempfile.mkdtemp(prefix="genztok_b200_data_")
+    except OSError:
+        root = tempfile.mkdtemp(prefix="genztok_b200_data_")
+    try:
+        _cache = unpack_into(root)
+        return _cache
+    except OSError:
+        pass
     raise RuntimeError("cannot unpack the bundled vocab/bpe.codes anywhere writable")

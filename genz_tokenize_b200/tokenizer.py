@@ -82,7 +82,9 @@ class Tokenize(object):
         self.unk_token = unk_token
         self._devices = devices
         self._extra_vocab = []
-        self._h = None
+        if getattr(self, "_h_dec", None):
+            self._close_decoder()
+        self._h = self._h_dec = None
         self._open()
 
     # ---- handle management ---------------------------------------------------------------------
@@ -103,6 +105,11 @@ class Tokenize(object):
         if self._extra_vocab:
             vocab = self._merged_vocab()
         rc = self._lib.genztok_create(os.fsencode(vocab), os.fsencode(self.bpe_file), sp, dev, len(devices), C.byref(h))
+        if self._extra_vocab:                                   # the merged copy was only for the loader
+            try:
+                os.unlink(vocab)
+            except OSError:
+                pass
         if rc:
             msg = (self._lib.genztok_last_error(None) or b"").decode("utf-8", "replace")
             if rc == L.E_IO:
@@ -113,6 +120,8 @@ class Tokenize(object):
         self._h = h
         self._ids = None
         self._encoder = self._decoder = self._bpe_ranks = None
+        if getattr(self, "_h_dec", None):
+            self._decoder = self._decoder_frozen
         for k, v in getattr(self, "_options", {}).items():
             self._set_option(k, v)
 
@@ -121,9 +130,21 @@ class Tokenize(object):
             self._lib.genztok_destroy(self._h)
         self._h = None
 
+    def _close_decoder(self):
+        if getattr(self, "_h_dec", None):
+            self._lib.genztok_destroy(self._h_dec)
+        self._h_dec = None
+
+    @property
+    def _hd(self):
+        """The handle whose tables `decode` reads: the one built by __init__ (tokenize.py:40 builds `decoder` there and nothing
+        refreshes it: add_vocab_file after construction leaves it stale), else the current one."""
+        return getattr(self, "_h_dec", None) or self._h
+
     def __del__(self):
         try:
             self._close()
+            self._close_decoder()
         except Exception:
             pass
 
@@ -196,11 +217,17 @@ class Tokenize(object):
         return path
 
     def add_vocab_file(self, vocab_file):
-        """tokenize.py:44-51: append another vocab file's words (the device tables are rebuilt)."""
+        """tokenize.py:44-51: append another vocab file's words to `encoder` (the device tables are rebuilt).  `decoder` is NOT
+        refreshed by the reference (it is built once, tokenize.py:40): ids added here decode to the unk token, and a word that
+        moved keeps decoding from its old id.  The handle of the tables as __init__ built them is kept for decoding."""
         with open(vocab_file, 'r', encoding='utf-8'):
             pass
         self._extra_vocab.append(vocab_file)
+        if getattr(self, "_h_dec", None) is None:
+            self._decoder_frozen = self.decoder                   # the dict as of construction
+            self._h_dec, self._h = self._h, None                  # (kept alive: _open() destroys only self._h)
         self._open()
+        self._decoder = self._decoder_frozen
 
     def add_bpe_file(self, bpe_file):
         """tokenize.py:53-57: replace the merge table (the device tables are rebuilt)."""
@@ -337,6 +364,8 @@ class Tokenize(object):
                 raise ValueError("None is not in list")                   # tokenize.py:157-159
             pad, _, eos = self._special_ids()[:3]
             conv = lambda a: [None if v == L.NONE else (eos if v == L.EOS_MARK else (pad if v == L.PAD_MARK else int(v))) for v in a]
+            if r._seq is None or (r._pad_mode and r._tt is None):
+                raise ValueError("row(): this batch was encoded without its sequence_id / token_type_ids planes (encode_batch(..., sequence_id=False / token_type_ids=False))")
             seq = conv(r._seq[s:s + int(r._seq_len[i])])
             result['sequence_id'] = seq
             if r._pad_mode:
@@ -430,17 +459,18 @@ class Tokenize(object):
         else:
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
             n, width = len(offsets) - 1, 0
-            flat = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1)
+            flat = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1) if ids.dtype.kind in "iu" and ids.dtype.itemsize <= 4 and ids.dtype != np.uint32 \
+                else self._ids_to_int32(ids.reshape(-1))                   # (an id of 2**32 + 5 is not id 5: it decodes to the unk token)
             offp = offsets.ctypes.data
         out = L.Text()
-        rc = self._lib.genztok_decode(self._h, flat.ctypes.data, offp, n, width, C.byref(out))
+        rc = self._lib.genztok_decode(self._hd, flat.ctypes.data, offp, n, width, C.byref(out))
         if rc:
             self._err(rc, "genztok_decode")
         try:
             off = np.ctypeslib.as_array(out.off, shape=(n + 1,)).copy()
             raw = C.string_at(out.bytes, int(out.total)) if out.total else b""
         finally:
-            self._lib.genztok_free_text(self._h, C.byref(out))
+            self._lib.genztok_free_text(self._hd, C.byref(out))
         return [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(n)]
 
     def encode_device(self, d_text, d_text_off, d_pair=None, d_pair_off=None, max_len=128, token_type_ids=True, sequence_id=False,
@@ -501,12 +531,12 @@ class Tokenize(object):
         out_off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
         total = C.c_int64()
         st = self._torch_stream(dev)
-        rc = self._lib.genztok_decode_device(self._h, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
+        rc = self._lib.genztok_decode_device(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
         if rc:
             self._err(rc, "genztok_decode_device")
         if out is None or out.numel() < max(total.value, 1) or out.device != dev or out.dtype != torch.uint8 or out.data_ptr() % 16:
             out = torch.empty((max(total.value, 1),), dtype=torch.uint8, device=dev)
-        rc = self._lib.genztok_decode_device(self._h, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), out.data_ptr(), None, st)
+        rc = self._lib.genztok_decode_device(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), out.data_ptr(), None, st)
         if rc:
             self._err(rc, "genztok_decode_device")
         return out[:total.value], out_off

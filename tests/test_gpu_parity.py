@@ -327,11 +327,24 @@ def test_decode_pad_runs(tok, oracle):
     any_rows = Tokenize()
     any_rows.set_option("no_fixed_decode", 1)            # widths that are a multiple of 4 through the warp-per-row kernels too
     any_rows.set_option("no_token_decode", 1)            # and ragged rows (a thread per id by default)
+    coop, lanes = Tokenize(), Tokenize()                 # both write kernels of the fixed-width family, whatever the average lead
+    coop.set_option("decode_write", 1)
+    lanes.set_option("decode_write", 2)
     for width in [1, 2, 3, 4, 7, 8, 9, 10, 11, 12, 16, 17, 31, 32, 33, 40, 64, 100, 124, 128, 132, 252, 255, 256, 257, 260, 300, 384, 516]:
         ids = _pad_run_rows(rng, 300, width, 0, 48423, exotic)
         ref = oracle.decode_batch(ids.reshape(-1), np.arange(0, 300 * width + 1, width, dtype=np.int64), threads=8)
         assert tok.decode_batch(ids) == ref, width
         assert any_rows.decode_batch(ids) == ref, width
+        assert coop.decode_batch(ids) == ref, width
+        assert lanes.decode_batch(ids) == ref, width
+    # encoder-shaped rows (short leads, long pad runs: the rows the lane-per-row kernel is for) at every alignment of the text
+    for width, lo, hi in [(128, 1, 14), (256, 10, 45), (64, 1, 40), (48, 0, 3)]:
+        ids = np.zeros((500, width), dtype=np.int32)
+        for r in range(500):
+            k = int(rng.integers(lo, hi + 1))
+            ids[r, :k] = rng.integers(1, 48423, k)
+        ref = oracle.decode_batch(ids.reshape(-1), np.arange(0, 500 * width + 1, width, dtype=np.int64), threads=8)
+        assert coop.decode_batch(ids) == ref and lanes.decode_batch(ids) == ref and tok.decode_batch(ids) == ref, width
     for n_rows in [1, 31, 32, 33, 64, 65]:                # tiles of 32 rows, whole and partial
         ids = _pad_run_rows(rng, n_rows, 128, 0, 48423, exotic)
         assert tok.decode_batch(ids) == oracle.decode_batch(ids.reshape(-1), np.arange(0, n_rows * 128 + 1, 128, dtype=np.int64)), n_rows
@@ -382,15 +395,18 @@ def test_decode_pad_run_vectors_from_the_reference():
     for b in load_decode_golden():
         if b["pad_token"] not in toks:
             sp = [b["pad_token"], "<s>", "</s>", "<mask>", "<unk>"]
-            t, a = Tokenize(*sp), Tokenize(*sp)
+            t, a, l2 = Tokenize(*sp), Tokenize(*sp), Tokenize(*sp)
             a.set_option("no_fixed_decode", 1)
+            t.set_option("decode_write", 1)
+            l2.set_option("decode_write", 2)
             assert t.encoder[b["pad_token"]] == b["pad_id"]
-            toks[b["pad_token"]] = (t, a)
-        t, a = toks[b["pad_token"]]
+            toks[b["pad_token"]] = (t, a, l2)
+        t, a, l2 = toks[b["pad_token"]]
         ids = np.array(b["ids"], dtype=np.int64).astype(np.int32)
         n, w = ids.shape
         assert t.decode_batch(ids) == b["out"], (b["pad_token"], w)
         assert a.decode_batch(ids) == b["out"], (b["pad_token"], w)
+        assert l2.decode_batch(ids) == b["out"], (b["pad_token"], w)
         assert t.decode_batch(ids.reshape(-1), np.arange(0, n * w + 1, w, dtype=np.int64)) == b["out"], (b["pad_token"], w)
 
 
@@ -751,3 +767,46 @@ def test_recycled_result_planes_hold_no_stale_columns(tok, oracle):
         assert_matches_oracle(be, oracle.encode_batch(ta, None, max_len=W, threads=8), what="recycled planes, singles")
     finally:
         tok.set_option("chunk_rows", 1 << 18)
+
+
+def test_add_vocab_and_bpe_file_after_construction(tmp_path):
+    """tokenize.py:44-57 called after __init__: `encoder` grows, `decoder` stays as built (added ids decode to the unk token),
+    `bpe_ranks` is replaced -- reference vectors (oracle/gen_golden_addvocab.py)."""
+    import gzip, json
+    from genz_tokenize_b200 import Tokenize
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "addvocab_v1.json.gz"), "rb") as f:
+        g = json.loads(f.read().decode("ascii"))
+    v2, c2 = tmp_path / "v2.txt", tmp_path / "c2.codes"
+    v2.write_text(g["vocab2"], encoding="utf-8")
+    c2.write_text(g["codes2"], encoding="utf-8")
+    tok = Tokenize(devices=[0])
+    assert tok.vocab_size() == g["n0"]
+    tok.add_vocab_file(str(v2))
+    s = g["steps"][0]
+    assert tok.vocab_size() == s["vocab_size"] and len(tok.decoder) == s["decoder_len"]
+    assert {w: tok.encoder.get(w) for w in s["enc"]} == s["enc"]
+    for c in s["calls"]:
+        assert tok(c["text"], max_len=12) == c["out"], c["text"]
+    for c in s["pairs"]:
+        assert tok(c["text"], c["pair"], max_len=16) == c["out"]
+    for d in s["decode"]:
+        assert tok.decode(d["ids"]) == d["out"], d["ids"]
+    tok.add_bpe_file(str(c2))
+    s = g["steps"][1]
+    assert tok.vocab_size() == s["vocab_size"] and len(tok.bpe_ranks) == s["n_ranks"]
+    for c in s["calls"]:
+        assert tok(c["text"], max_len=12) == c["out"], c["text"]
+    for b in s["bpe"]:
+        assert tok.bpe(b["w"]) == b["out"], b["w"]
+    for d in s["decode"]:
+        assert tok.decode(d["ids"]) == d["out"], d["ids"]
+    import glob, tempfile
+    assert not glob.glob(os.path.join(tempfile.gettempdir(), "genztok_vocab_*.txt")), "merged vocab copies must not pile up"
+
+
+def test_decode_batch_ids_beyond_int32_are_unknown(tok):
+    ids = np.array([2 ** 32 + 5, 770, -(2 ** 40), 5], dtype=np.int64)
+    assert tok.decode_batch(ids, np.array([0, 4], dtype=np.int64)) == [tok.decode(ids.tolist())] == ["<unk> sinh_viên <unk> " + tok.decoder[5]]
+    be = tok.encode_batch(["xin chào"], ["hello"], max_len=8, sequence_id=False)
+    with pytest.raises(ValueError):
+        be.row(0)
