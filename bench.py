@@ -624,7 +624,23 @@ def run_extras(torch, tok, S, dev, peak, workload, Tokenize):
     extra["configs1_decode_128"] = {"workload": "decode of the [1M,128] planes of configs[1]", "ms": dms1, "rows_per_s": n1 / (dms1 * 1e-3), "text_bytes": db1,
                                     "alg_gb_per_s": dalg1 / (dms1 * 1e-3) / 1e9, "hbm_frac": dalg1 / (dms1 * 1e-3) / 1e9 / peak,
                                     "note": "includes the allocation of the text tensor and the device->host read of its size"}
-    del t1, o1, holder
+    # the reference's DEFAULT call shape (tokenize.py:184-190: max_len=None -> no padding, no truncation): ragged rows through the
+    # host API (there is no padded plane to hold them on the device); kernels by the library's CUDA events, the call by wall clock
+    h1 = (t1[:b1].cpu().numpy(), o1.cpu().numpy())
+    tok.encode_batch(h1)                                            # allocations
+    tok.set_profiling(True); tok.profile_report(reset=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    rg = tok.encode_batch(h1)
+    call_ms = (time.perf_counter() - t0) * 1e3
+    rprof = tok.profile_report(reset=True); tok.set_profiling(False)
+    rtok = int(rg["real_tokens"])
+    ralg = b1 + 8 * (n1 + 1) + 5 * rtok + 8 * (n1 + 1)              # SURVEY.md 8 d4, ragged: utf8 + offsets in, 5 B per token + row offsets out
+    rk_ms = sum(v["ms"] for v in rprof.values())
+    extra["default_call_ragged"] = {"workload": "the 1,048,576 single sentences with max_len=None (ragged rows: ids + mask + int64 row offsets), Tokenize.encode_batch, host buffers",
+                                    "kernels_ms": rk_ms, "call_ms": call_ms, "tokens_per_s_kernels": rtok / (rk_ms * 1e-3), "tokens_per_s_call": rtok / (call_ms * 1e-3),
+                                    "alg_gb_per_s_kernels": ralg / (rk_ms * 1e-3) / 1e9, "hbm_frac_kernels": ralg / (rk_ms * 1e-3) / 1e9 / peak,
+                                    "kernels": {k: round(v["ms"], 4) for k, v in rprof.items() if v["ms"] > 0.005}}
+    del rg, t1, o1, holder
     # configs[4]: custom vocab / merges, long documents, max_len 4096, low word reuse -- reported cold (its definition) and warm
     import tempfile
     with tempfile.TemporaryDirectory() as td:

@@ -138,6 +138,7 @@ struct genztok {
     // pinned host pool
     std::multimap<size_t, void*> host_pool;
     size_t host_pool_bytes = 0;
+    std::mutex pool_mu;                  // guards host_pool (the device worker threads of a call take staging buffers from it)
     // What a pooled result plane still holds from its last use: the same [rows, width] shape with everything behind column
     // `dirty_cols` equal to padding.  A call that reuses it copies only the columns that can differ (see encode_fixed_pipelined).
     struct PlaneMeta { int64_t rows; int32_t width, dirty_cols, elt; int32_t pad; };
@@ -634,19 +635,57 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     return stream_leave(h, d, st);
 }
 
-void* host_pool_get(genztok_t* h, size_t bytes) {
+void* host_pool_get(genztok_t* h, size_t bytes, size_t* got = nullptr) {
     if (bytes == 0) bytes = 16;
-    auto it = h->host_pool.lower_bound(bytes);
-    if (it != h->host_pool.end() && it->first <= bytes + bytes / 4 + 4096) {
-        void* p = it->second;
-        h->host_pool_bytes -= it->first;
-        h->host_pool.erase(it);
-        return p;
+    {
+        std::lock_guard<std::mutex> l(h->pool_mu);
+        auto it = h->host_pool.lower_bound(bytes);
+        if (it != h->host_pool.end() && it->first <= bytes + bytes / 4 + 4096) {
+            void* p = it->second;
+            if (got) *got = it->first;
+            h->host_pool_bytes -= it->first;
+            h->host_pool.erase(it);
+            return p;
+        }
     }
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (got) *got = bytes;
     return p;
 }
+void host_pool_put(genztok_t* h, void* p, size_t bytes) {
+    std::lock_guard<std::mutex> l(h->pool_mu);
+    if (h->host_pool_bytes + bytes > (size_t)8 << 30) { h->plane_meta.erase(p); cudaFreeHost(p); return; }
+    h->host_pool.insert({bytes, p});
+    h->host_pool_bytes += bytes;
+}
+
+// A growable array in pinned host memory (from the handle's pool): what a device worker collects ragged results in.  Device to
+// host copies into pageable memory are staged by the driver at a fraction of the link's rate; resize() does not initialise.
+template <class T>
+struct PinnedVec {
+    genztok_t* h = nullptr; T* p = nullptr; size_t n = 0, cap_bytes = 0;
+    PinnedVec() = default;
+    PinnedVec(const PinnedVec&) = delete;
+    PinnedVec& operator=(const PinnedVec&) = delete;
+    ~PinnedVec() { if (p) host_pool_put(h, p, cap_bytes); }
+    bool resize(size_t m) {
+        if (m * sizeof(T) > cap_bytes) {
+            size_t got = 0;
+            const size_t want = std::max<size_t>(m * sizeof(T) + m * sizeof(T) / 2, 1 << 16);
+            T* q = reinterpret_cast<T*>(host_pool_get(h, (want + 4095) & ~(size_t)4095, &got));
+            if (!q) return false;
+            if (n) memcpy(q, p, n * sizeof(T));
+            if (p) host_pool_put(h, p, cap_bytes);
+            p = q; cap_bytes = got;
+        }
+        n = m;
+        return true;
+    }
+    T* data() { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
 
 struct OutBlock {
     std::vector<std::pair<void*, size_t>> pinned;   // returned to the pool on free
@@ -903,8 +942,7 @@ void genztok_free_encoded(genztok_t* h, genztok_encoded_t* out) {
     {
         std::lock_guard<std::mutex> lk(h->mu);
         for (auto& pr : ob->pinned) {
-            if (h->host_pool_bytes + pr.second > (size_t)8 << 30) { h->plane_meta.erase(pr.first); cudaFreeHost(pr.first); }
-            else { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+            host_pool_put(h, pr.first, pr.second);
         }
     }
     for (void* p : ob->mallocs) free(p);
@@ -932,8 +970,9 @@ struct EncodePart {
     std::string err;
     int32_t extent = 0;            // fixed layout: columns that can differ from padding, max over this part's chunks
     int64_t d2h_bytes = 0;
-    std::vector<int32_t> ids, spans; std::vector<uint8_t> mask; std::vector<int8_t> tt, seq;
+    PinnedVec<int32_t> ids, spans; PinnedVec<uint8_t> mask; PinnedVec<int8_t> tt, seq;
     int64_t total = 0, span_total = 0, tokens = 0;
+    void bind(genztok_t* h) { ids.h = h; spans.h = h; mask.h = h; tt.h = h; seq.h = h; }
 };
 
 void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64_t rb, int64_t re, EncodePart* part) {
@@ -1155,8 +1194,9 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         CUF(cudaGetLastError());
         // bring the chunk home; offsets are kept relative to this device's part
         const size_t old = part->ids.size();
-        part->ids.resize(old + (size_t)total); part->mask.resize(old + (size_t)total);
-        if (has_pair) { part->tt.resize(old + (size_t)total); part->seq.resize(old + (size_t)total); }
+        bool grown = part->ids.resize(old + (size_t)total) && part->mask.resize(old + (size_t)total);
+        if (has_pair) grown = grown && part->tt.resize(old + (size_t)total) && part->seq.resize(old + (size_t)total);
+        if (!grown) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
         std::vector<int64_t> offs((size_t)m + 1);
         if (total) {
             CUF(cudaMemcpyAsync(part->ids.data() + old, d->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
@@ -1170,7 +1210,7 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         if (want_spans) {
             soffs.resize((size_t)m + 1);
             const size_t so = part->spans.size();
-            part->spans.resize(so + (size_t)span_n * 2);
+            if (!part->spans.resize(so + (size_t)span_n * 2)) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
             if (span_n) CUF(cudaMemcpyAsync(part->spans.data() + so, d->spans.p, (size_t)span_n * 8, cudaMemcpyDeviceToHost, st));
             CUF(cudaMemcpyAsync(soffs.data(), d->span_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
@@ -1222,7 +1262,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
     out->_owner = ob;
     out->n = n; out->has_pair = has_pair;
     auto free_nolock = [&]() {
-        for (auto& pr : ob->pinned) { h->plane_meta.erase(pr.first); h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        for (auto& pr : ob->pinned) { h->plane_meta.erase(pr.first); host_pool_put(h, pr.first, pr.second); }
         for (void* p : ob->mallocs) free(p);
         delete ob;
         memset(out, 0, sizeof *out);
@@ -1276,6 +1316,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         }
     }
     std::vector<EncodePart> parts((size_t)G);
+    for (auto& pt : parts) pt.bind(h);
     if (G == 1 || n < 2 * G) {
         if (G > 1) { for (int g = 1; g <= G; g++) dcut[(size_t)g] = n; }
         encode_rows_on_device(h, h->devs[0], J, 0, n, &parts[0]);
@@ -1474,7 +1515,7 @@ void genztok_free_text(genztok_t* h, genztok_text_t* out) {
     OutBlock* ob = reinterpret_cast<OutBlock*>(out->_owner);
     {
         std::lock_guard<std::mutex> lk(h->mu);
-        for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+        for (auto& pr : ob->pinned) host_pool_put(h, pr.first, pr.second);
     }
     for (void* p : ob->mallocs) free(p);
     delete ob;
@@ -1561,7 +1602,7 @@ int genztok_decode(genztok_t* h, const int32_t* ids, const int64_t* ids_off, int
     }
     for (auto& pt : parts)
         if (pt.rc) {
-            for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; }
+            for (auto& pr : ob->pinned) host_pool_put(h, pr.first, pr.second);
             delete ob;
             return pt.rc;
         }
@@ -1597,7 +1638,7 @@ int genztok_preprocess(genztok_t* h, int op, const uint8_t* text, const int64_t*
     std::vector<uint8_t> acc;
     int64_t total_all = 0;
     int rc = GENZTOK_OK;
-    auto bail = [&](int code) { for (auto& pr : ob->pinned) { h->host_pool.insert({pr.second, pr.first}); h->host_pool_bytes += pr.second; } delete ob; return code; };
+    auto bail = [&](int code) { for (auto& pr : ob->pinned) host_pool_put(h, pr.first, pr.second); delete ob; return code; };
     int64_t r0 = 0;
     while (r0 < n) {
         int64_t r1 = std::min<int64_t>(n, r0 + h->chunk_rows);
@@ -1723,6 +1764,37 @@ int genztok_check_errors(genztok_t* h, int dev, void* stream, int64_t* n_errors)
     CU(cudaStreamSynchronize(st));
     *n_errors = (int64_t)nerr;
     return nerr ? fail(h, GENZTOK_E_CUDA, "device pipeline reported %llu inconsistencies", nerr) : GENZTOK_OK;
+}
+
+// Device form of the normalisers: text and offsets already on the device, the result stays there (so that it can be handed to
+// genztok_encode_device on the same stream: normalise -> tokenise without crossing PCIe).  Two steps like genztok_decode_device.
+int genztok_preprocess_device(genztok_t* h, int dev, int op, const uint8_t* d_text, const int64_t* d_text_off, int64_t n, int64_t* d_out_off,
+                              uint8_t* d_out, int64_t* total_bytes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_text_off || !d_out_off || op < 0 || op > 4) return fail(h, GENZTOK_E_INVALID, "genztok_preprocess_device: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    LaunchScope::cur_stream = st;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)d->sm_count * 8));
+    if (!d_out) {
+        CU(d->out_len.ensure((size_t)std::max<int64_t>(n, 1) * 8));
+        PrepArgs A{d_text, d_text_off, n, op, d->out_len.as<int64_t>(), nullptr, nullptr};
+        if (n > 0) { LaunchScope ls(h, d, "k_prep_len"); k_prep<false><<<grid, 256, 0, st>>>(A); }
+        int rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d_out_off, n);
+        if (rc) return rc;
+        if (total_bytes) {
+            CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        return GENZTOK_OK;
+    }
+    PrepArgs A{d_text, d_text_off, n, op, nullptr, d_out_off, d_out};
+    if (n > 0) { LaunchScope ls(h, d, "k_prep_write"); k_prep<true><<<grid, 256, 0, st>>>(A); }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
 }
 
 // ---- helpers ----------------------------------------------------------------------------------------------

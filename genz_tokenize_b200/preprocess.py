@@ -40,6 +40,28 @@ def run_batch(op, texts, tok=None):
     return [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(n)]
 
 
+def run_device(op, d_text, d_text_off, tok=None):
+    """One normaliser over documents that are already on the GPU (torch uint8 bytes + int64 offsets[n+1]); returns
+    (uint8 bytes padded for the encoder's 16-byte loads, int64 offsets, byte count) on the same device, written on torch's
+    current stream -- ready for `Tokenize.encode_device` without a trip through host memory."""
+    import torch
+    tok = tok or _ctx()
+    n = d_text_off.numel() - 1
+    dev = d_text.device
+    st = tok._torch_stream(dev)
+    off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    total = C.c_int64()
+    rc = tok._lib.genztok_preprocess_device(tok._h, 0, int(op), d_text.data_ptr(), d_text_off.data_ptr(), n, off.data_ptr(), None, C.byref(total), st)
+    if rc:
+        tok._err(rc, "genztok_preprocess_device")
+    nb = int(total.value)
+    out = torch.zeros((nb + (-nb) % 16 + 32,), dtype=torch.uint8, device=dev)
+    rc = tok._lib.genztok_preprocess_device(tok._h, 0, int(op), d_text.data_ptr(), d_text_off.data_ptr(), n, off.data_ptr(), out.data_ptr(), None, st)
+    if rc:
+        tok._err(rc, "genztok_preprocess_device")
+    return out, off, nb
+
+
 def _one(op, txt):
     if not isinstance(txt, str):
         raise TypeError("expected string or bytes-like object, got %r" % type(txt).__name__)

@@ -172,6 +172,11 @@ int genztok_attention_mask(genztok_t *h, const int32_t *ids, int64_t n, uint8_t 
 #define GENZTOK_PREP_REMOVE_URL 4         /* remove_URL         preprocess.py:75-80 */
 /* One normaliser over a batch of documents (packed UTF-8 + offsets in, the same out). */
 int genztok_preprocess(genztok_t *h, int op, const uint8_t *text, const int64_t *text_off, int64_t n, genztok_text_t *out);
+/* Device form: text in, text out, both on the device, on `stream` -- the result can go straight into genztok_encode_device.
+ * Step 1 (d_out == NULL): fills d_out_off[n+1], returns the total in *total_bytes (synchronises).  Step 2: writes the text
+ * (the caller allocates total + 32 bytes, 16-byte aligned, so that the encoder's 16-byte loads stay inside). */
+int genztok_preprocess_device(genztok_t *h, int dev, int op, const uint8_t *d_text, const int64_t *d_text_off, int64_t n,
+                              int64_t *d_out_off, uint8_t *d_out, int64_t *total_bytes, void *stream);
 
 /* ---- utilities -------------------------------------------------------------------------------- */
 void *genztok_host_alloc(size_t bytes); /* pinned host memory for inputs */

@@ -54,3 +54,33 @@ def test_device_matches_oracle_on_large_batches():
     docs = [d + deco[int(rng.integers(0, len(deco)))] + d[: int(rng.integers(0, 30))] for d in docs]
     for op in range(5):
         assert P.run_batch(op, docs, tok=tok) == O.preprocess(op, docs), NAMES[op]
+
+
+@pytest.mark.gpu
+def test_device_resident_chain_normalise_then_tokenise(pgold):
+    """genztok_preprocess_device: text in, text out, both on the GPU -- the same bytes as the host form -- and straight into
+    encode_device on the same stream: normalise -> tokenise without a trip through host memory."""
+    import torch
+    from genz_tokenize_b200 import preprocess as P, workload
+    from genz_tokenize_b200.tokenizer import Tokenize, pack_strings
+    from oracle import oracle as O
+    from oracle.oracle import Oracle
+    tok = Tokenize(devices=[0])
+    dev = torch.device("cuda:0")
+    docs = workload.unpack(*workload.generate_hashed(9, 0, 6000, 0, 0, 30, 0.1))
+    rng = np.random.default_rng(4)
+    deco = ["<p>", "</p>", "http://a.b/c ", " 😀 ", "!", "à", "　", " <br/> "]
+    docs = [d + deco[int(rng.integers(0, len(deco)))] + d[: int(rng.integers(0, 20))] for d in docs] + list(pgold["texts"])
+    tb, to = pack_strings(docs)
+    d_t = torch.from_numpy(np.concatenate([tb, np.zeros(32, dtype=np.uint8)])).to(dev)
+    d_o = torch.from_numpy(to).to(dev)
+    for op in (P.REMOVE_HTML, P.REMOVE_URL, P.REMOVE_EMOJI):
+        out, off, nb = P.run_device(op, d_t, d_o, tok=tok)
+        want = O.preprocess(op, docs)
+        wb, wo = pack_strings(want)
+        assert nb == len(wb) and np.array_equal(off.cpu().numpy(), wo) and np.array_equal(out[:nb].cpu().numpy(), wb), NAMES[op]
+        enc = tok.encode_device(out, off, max_len=64, text_bytes=nb)        # chained on the device
+        torch.cuda.synchronize()
+        ref = Oracle().encode_batch((wb, wo), None, max_len=64, threads=8)
+        assert np.array_equal(enc["input_ids"].cpu().numpy().reshape(-1), ref["ids"]), NAMES[op]
+        assert np.array_equal(enc["attention_mask"].cpu().numpy().reshape(-1), ref["mask"]), NAMES[op]
