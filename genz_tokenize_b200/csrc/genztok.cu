@@ -124,6 +124,7 @@ struct genztok {
     int64_t decode_write = 0;            // fixed-width decode, write pass: 0 = by the average lead, 1 = warp per row, 2 = lane per row (test knob)
     int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
     int64_t copy_blocks = 64;            // blocks of k_copy_out
+    int64_t copy_round = 64;             // columns the one-byte planes' copy-out is rounded up to (32 or 64: whole 64-byte lines of host memory)
     int64_t l2_policy = 0;               // bit 0: text read evict-first, bit 1: word arrays stored evict-last (k_flat_words; experiments)
     int64_t rows_pad_pct = 0;            // share of the pad columns (percent of the 32-row tiles, the last ones) that k_flat_rows stores instead of k_flat_words
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
@@ -843,6 +844,9 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->decode_write = value;
     } else if (n == "no_copy_kernel") {
         h->no_copy_kernel = value;
+    } else if (n == "copy_round") {
+        if (value != 32 && value != 64) return fail(h, GENZTOK_E_INVALID, "copy_round must be 32 or 64");
+        h->copy_round = value;
     } else if (n == "copy_blocks") {
         if (value < 1 || value > 4096) return fail(h, GENZTOK_E_INVALID, "copy_blocks must be in 1..4096");
         h->copy_blocks = value;
@@ -1085,7 +1089,9 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
             CopyOutArgs CO{};
             CO.m = m;
             auto copy_plane = [&](void* host, const void* dev, size_t elt, int32_t old_dirty) -> cudaError_t {
-                const int32_t cols = std::min<int32_t>(max_len, (std::max(kc, old_dirty) + 31) & ~31);
+                // whole 64-byte lines of host memory for the one-byte planes too (a partial line is a read-modify-write for the host)
+                const int32_t rnd = elt == 1 ? (int32_t)std::max<int64_t>(32, h->copy_round) : 32;
+                const int32_t cols = std::min<int32_t>(max_len, (std::max(kc, old_dirty) + rnd - 1) / rnd * rnd);
                 part->d2h_bytes += (int64_t)m * cols * (int64_t)elt;
                 uint8_t* dst = reinterpret_cast<uint8_t*>(host) + o0 * elt;
                 if (cols >= max_len) return cudaMemcpyAsync(dst, dev, (size_t)m * (size_t)max_len * elt, cudaMemcpyDeviceToHost, d->s_out);
@@ -1335,7 +1341,7 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         int32_t extent = 1;
         for (auto& pt : parts) extent = std::max(extent, pt.extent);
         for (int k = 0; k < 4; k++)
-            if (planes4[k]) h->plane_meta[planes4[k]] = genztok::PlaneMeta{n, max_len, std::min<int32_t>(max_len, (extent + 31) & ~31), elts4[k], 0};
+            if (planes4[k]) h->plane_meta[planes4[k]] = genztok::PlaneMeta{n, max_len, std::min<int32_t>(max_len, (extent + 31) & ~31), elts4[k], 0};   // (a lower bound of what was copied is enough: the columns behind it hold padding either way)
         if (J.want_tt) for (int64_t r = 0; r < n; r++) out->tt_len[r] = max_len;
     } else {
         // stitch the parts: shift every part's row offsets by what came before it, concatenate the flat planes
