@@ -26,6 +26,7 @@ struct DevTables {
     const uint8_t* form_blob;
     const uint32_t *mid_off, *mid_len, *last_off, *last_len;
     const uint32_t *mid_desc, *last_desc;   // (offset/8) << 8 | min(len,255)
+    const uint4* mid_fast;                  // a mid form of up to 15 bytes and, in byte 15, its length (255: longer, see mid_desc)
     int32_t n_ids;
 };
 

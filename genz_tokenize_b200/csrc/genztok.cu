@@ -121,7 +121,8 @@ struct genztok {
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
-    int64_t decode_write = 0;            // fixed-width decode, write pass: 0 = by the average lead, 1 = warp per row, 2 = lane per row (test knob)
+    int64_t decode_write = 0;            // fixed-width decode, write pass: 0 = by the average lead, 1 = warp per row, 2 / 3 = lane per junction with 256 / 512 bytes (test knob)
+    int64_t decode_wide_max = 0;         // average lead (ids) up to which the 512-byte junction kernel is taken (0: never)
     int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
     int64_t copy_blocks = 64;            // blocks of k_copy_out
     int64_t copy_round = 64;             // columns the one-byte planes' copy-out is rounded up to (32 or 64: whole 64-byte lines of host memory)
@@ -250,6 +251,7 @@ int init_device(genztok_t* h, DeviceCtx* d) {
     CU(upload(d, H.last_len, &T.last_len));
     CU(upload(d, H.mid_desc, &T.mid_desc));
     CU(upload(d, H.last_desc, &T.last_desc));
+    { const HostTables::FastForm* ff = nullptr; CU(upload(d, H.mid_fast, &ff)); T.mid_fast = reinterpret_cast<const uint4*>(ff); }
     T.n_ids = (int32_t)H.n_ids;
     T.pad = H.special_id[0]; T.bos = H.special_id[1]; T.eos = H.special_id[2]; T.msk = H.special_id[3]; T.unk = H.special_id[4];
     T.specials_distinct = (T.pad != T.bos && T.pad != T.eos && T.bos != T.eos) ? 1 : 0;
@@ -842,6 +844,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         h->pad_box_cols = value;
     } else if (n == "decode_write") {
         h->decode_write = value;
+    } else if (n == "decode_wide_max") {
+        h->decode_wide_max = value;
     } else if (n == "no_copy_kernel") {
         h->no_copy_kernel = value;
     } else if (n == "copy_round") {
@@ -1482,21 +1486,28 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
     }
     // the write pass reads what the length pass of the same batch left in dec_lead; after another batch's length pass it is redone
     if (!same_batch(0)) { int rc = length_pass(); if (rc) return rc; }
-    // Two write kernels for fixed-width rows: a lane per row assembles short leads (single sentences, ~10 pieces in front of the
-    // pad run); the whole warp gathers long ones 32 pieces at a time (sentence pairs, ~20).  The length pass counted the pieces.
-    const bool by_lanes = h->decode_write == 2 || (h->decode_write == 0 && d->dec_avg_lead >= 0 && d->dec_avg_lead <= 14.0);
-    if (n > 0 && fixed && !by_lanes) {
+    // Two write kernels for fixed-width rows: a lane per junction of two rows assembles short leads (single sentences, ~10 pieces in
+    // front of the pad run); the whole warp gathers long ones 32 pieces at a time (sentence pairs, ~20).  The length pass counted the pieces.
+    const int by_lanes = h->decode_write == 2 ? 1 : h->decode_write == 3 ? 2 : h->decode_write == 1 ? 0
+                         : d->dec_avg_lead < 0 ? 0 : d->dec_avg_lead <= 14.0 ? 1 : d->dec_avg_lead <= (double)h->decode_wide_max ? 2 : 0;
+    auto launch_junctions = [&](auto kern, int stride, int warps) -> int {
+        const size_t smem = (size_t)warps * (32 * (size_t)stride + 16);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+        const int64_t per_block = 32 * warps;
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 1 + per_block - 1) / per_block, (int64_t)d->sm_count * std::max(occ, 1)));   // n + 1 junctions
+        LaunchScope ls(h, d, "k_decode_write_fixed");
+        kern<<<grid, warps * 32, smem, st>>>(d->T, A);
+        return GENZTOK_OK;
+    };
+    if (n > 0 && fixed && by_lanes == 0) {
         LaunchScope ls(h, d, "k_decode_write_fixed");
         k_decode_write_fixed_coop<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * 5)), 256, 0, st>>>(d->T, A);
+    } else if (n > 0 && fixed && by_lanes == 1) {
+        int rc = launch_junctions(k_decode_write_fixed<256, 8, 3>, 256, 8); if (rc) return rc;
     } else if (n > 0 && fixed) {
-        const size_t smem = 8 * (32 * (size_t)DWF_STRIDE + 16);
-        static bool attr_set = false;
-        if (!attr_set) { CU(cudaFuncSetAttribute(k_decode_write_fixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-        int occ = 1;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode_write_fixed, 256, smem));
-        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * std::max(occ, 1)));
-        LaunchScope ls(h, d, "k_decode_write_fixed");
-        k_decode_write_fixed<<<grid, 256, smem, st>>>(d->T, A);
+        int rc = launch_junctions(k_decode_write_fixed<512, 4, 3>, 512, 4); if (rc) return rc;
     }
     else if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode_write<<<grid_write, 256, 0, st>>>(d->T, A); }
     CU(cudaGetLastError());

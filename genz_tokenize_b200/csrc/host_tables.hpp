@@ -84,6 +84,8 @@ struct HostTables {
     std::vector<uint8_t> form_blob;
     std::vector<uint32_t> mid_off, mid_len, last_off, last_len;
     std::vector<uint32_t> mid_desc, last_desc;    // (offset/8) << 8 | min(len,255): one load per id on the device
+    struct FastForm { uint32_t w[4]; };           // a "followed by another piece" form of up to 15 bytes with its length in the top byte (255: see the blob)
+    std::vector<FastForm> mid_fast;               // the form and its length in ONE 16-byte load
     uint32_t max_form = 0;                        // longest decode form in bytes
     int64_t n_ids = 0;
 
@@ -341,6 +343,16 @@ struct HostTables {
         for (int64_t id = 0; id <= n_ids; id++) {
             mid_desc[(size_t)id] = ((mid_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(mid_len[(size_t)id], 255u);
             last_desc[(size_t)id] = ((last_off[(size_t)id] / 8) << 8) | std::min<uint32_t>(last_len[(size_t)id], 255u);
+        }
+        mid_fast.assign((size_t)n_ids + 1, FastForm{{0, 0, 0, 0}});
+        for (int64_t id = 0; id <= n_ids; id++) {
+            FastForm& f = mid_fast[(size_t)id];
+            const uint32_t len = mid_len[(size_t)id];
+            if (len > 15) { f.w[3] = 255u << 24; continue; }
+            uint8_t b[16] = {0};
+            std::memcpy(b, form_blob.data() + mid_off[(size_t)id], len);
+            b[15] = (uint8_t)len;
+            std::memcpy(f.w, b, 16);
         }
         while (form_blob.size() % 16) form_blob.push_back(0);
         return true;

@@ -636,123 +636,182 @@ __global__ void __launch_bounds__(256, 5) k_decode_write_fixed_coop(DevTables T,
     }
 }
 
-// Pass 2 for fixed-width rows with short leads (single sentences: ~10 pieces).  A warp takes 32 consecutive rows.
-//  A. A LANE PER ROW assembles the text of the ids in front of the row's trailing pad run (the "lead": ~20 pieces, ~130 bytes
-//     for a sentence pair) in shared memory -- piece after piece, eight bytes a store round, at the row's alignment in the
-//     output (g0 & 15), and fills it up to the next 16-byte boundary with the beginning of the pad run's periodic text.
-//  B. The WARP then writes each row with aligned 16-byte stores, a lane per unit: the lead units from shared memory, the run's
-//     units from the table of the periodic text by phase; the row's first partial unit (shared with the row before) and its
-//     tail (rest of the run + the last piece) go bytewise.
-//  Rows without a usable pad run, with a long lead or a very long vocabulary entry take the general row routine afterwards.
-// 330 -> ~100 warp instructions per row: the write pass was bound by instruction issue, not by memory.
-static const int DWF_STRIDE = 256;      // bytes of shared memory per row (a multiple of 16: the units are read back as 16-byte vectors)
-static const int DWF_LEADMAX = 184;     // longest lead (bytes) assembled there: 15 (alignment) + lead + 15 (fill) + 15 + 24 (tail) <= 256
-static const int DWF_LASTMAX = 24;      // longest last piece on the fast path
-struct __align__(16) DwfRow { long long g0; uint16_t nrun; uint8_t nl, q0, tail, fast; uint16_t s_bytes; };
-__global__ void __launch_bounds__(256, 3) k_decode_write_fixed(DevTables T, DecArgs A) {
+// Pass 2 for fixed-width rows with short leads (single sentences: ~10 pieces in front of the pad run).  The text of consecutive
+// rows is contiguous, so the output is cut at 16-byte boundaries inside the pad runs instead of at the rows: JUNCTION j is what
+// lies between the last whole unit of row j-1's run and the first whole unit of row j's run -- the rest of run j-1, the last
+// piece of row j-1, the pieces in front of row j's run (its "lead") and the first bytes of run j up to the next boundary.
+// It begins and ends on a unit boundary, so every byte of the batch leaves in an aligned 16-byte store.
+//  A. A LANE PER JUNCTION assembles it in shared memory from the two rows' descriptions (pass 1) -- the bytes go through a
+//     64-bit accumulator and land as aligned 8-byte words; the 16-byte units of a junction are permuted by its lane number so
+//     that neither these stores nor the unit loads of part B meet in one bank.
+//  B. The WARP writes each junction and the whole units of the run behind it, a lane per unit.
+//  Rows without a usable run, with a long lead or a long last piece are written whole by the general row routine afterwards
+//  (a junction next to such a row starts or ends inside a unit: that unit goes bytewise).  There are n_rows + 1 junctions.
+// STRIDE: bytes of shared memory per junction (16 or 32 units); the longest lead assembled there is STRIDE - 72:
+// 15 (rest of the run before) + 24 (last piece) + lead + 15 (fill) <= STRIDE.
+static const uint32_t DWJ_LASTMAX = 24;     // longest last piece
+static const uint32_t DWJ_MINRUN = 48;      // shortest run (bytes): the two junctions around it must not meet
+struct __align__(16) DwjInfo { long long base; uint32_t nrun; uint8_t nu, a, e, q0; };   // base: global offset of unit 0; a / e: first / last unit partial
+__device__ __forceinline__ bool dwj_tail_ok(const uint4 ld, int W, uint32_t L, uint32_t* run_total) {
+    const int32_t n_lead = (int32_t)ld.x;
+    *run_total = n_lead >= 0 ? (uint32_t)(W - 1 - n_lead) * L : 0u;
+    return n_lead >= 0 && *run_total >= DWJ_MINRUN && ld.w <= DWJ_LASTMAX;
+}
+template <int STRIDE, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTables T, DecArgs A) {
+    constexpr int DWJ_STRIDE = STRIDE, DWJ_LEADMAX = STRIDE - 72;
+    constexpr uint32_t UMASK = STRIDE / 16 - 1;
     extern __shared__ __align__(16) uint8_t dwf_smem[];
-    __shared__ __align__(16) uint8_t padtab[8][8][16];
-    __shared__ DwfRow rowinfo[8][32];
+    __shared__ __align__(16) uint8_t padtab[WARPS][8][16];
+    __shared__ DwjInfo info[WARPS][32];
     const int wib = threadIdx.x >> 5;
-    uint8_t* const leadbuf = dwf_smem + (size_t)wib * (32 * DWF_STRIDE + 16);            // [32][DWF_STRIDE]; the general routine's staging buffer aliases it
-    const DecWarp w = dec_warp_setup(T, reinterpret_cast<uint8_t (*)[DEC_CAP + 16]>(dwf_smem), padtab);
-    DecWarp wg = w;
-    wg.ob = leadbuf;
+    uint8_t* const jbuf = dwf_smem + (size_t)wib * (32 * DWJ_STRIDE + 16);             // [32][STRIDE]; the general routine's staging buffer aliases it
+    DecWarp w = dec_warp_setup(T, reinterpret_cast<uint8_t (*)[DEC_CAP + 16]>(dwf_smem), padtab);
+    w.ob = jbuf;
     const int lane = w.lane;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const bool use_lead = A.lead != nullptr && w.padL != 0;
     const int W = A.width;
     const uint32_t L = w.padL, nid = (uint32_t)T.n_ids;
-    const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
+    const uint64_t n_tiles = ((uint64_t)A.n_rows + 1 + 31) >> 5;
+    const uint32_t sw = (uint32_t)lane & UMASK;
+    const uint32_t lane_ph = L ? dec_mod(16u * (uint32_t)lane, L, w.padM) : 0u;
+    uint8_t* const mine = jbuf + lane * DWJ_STRIDE;
     for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
-        const int64_t r0 = (int64_t)tile * 32;
-        const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
-        // ---- A. my row (a lane per row): its lead, the fill up to the next unit and its tail into shared memory
-        {
-            DwfRow me; me.g0 = 0; me.nrun = 0; me.nl = 0; me.q0 = 0; me.tail = 0; me.fast = 0; me.s_bytes = 0;
-            uint4 ld = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-            if (lane < rows) {
-                me.g0 = A.out_off[r0 + lane];
-                if (use_lead) ld = *reinterpret_cast<const uint4*>(A.lead + r0 + lane);
-                const int32_t n_lead = (int32_t)ld.x;
-                const uint32_t run_total = n_lead >= 0 ? (uint32_t)(W - 1 - n_lead) * L : 0u;
-                bool fast = n_lead >= 0 && ld.y <= (uint32_t)DWF_LEADMAX && run_total >= 32u && ld.w <= (uint32_t)DWF_LASTMAX;
-                if (fast) {
-                    const int32_t* rid = A.ids + (r0 + lane) * (int64_t)W;
-                    uint8_t* sb = leadbuf + lane * DWF_STRIDE;
-                    const uint32_t a = (uint32_t)(me.g0 & 15);
-                    uint32_t pos = a;
-                    for (int32_t i0 = 0; i0 < n_lead && fast; i0 += 4) {
-                        const int4 v4 = *reinterpret_cast<const int4*>(rid + i0);        // (W is a multiple of 4 and the rows are 16-byte aligned)
-                        const int32_t idv[4] = {v4.x, v4.y, v4.z, v4.w};
+        const int64_t j0 = (int64_t)tile * 32, jj = j0 + lane;
+        // ---- A. my junction: between row jj - 1 and row jj
+        const bool has_prev = jj >= 1 && jj <= A.n_rows, has_cur = jj < A.n_rows;
+        uint4 ldp = make_uint4(0xFFFFFFFFu, 0, 0, 0), ldc = ldp;
+        long long g0p = 0, g0c = 0;
+        if (has_prev) { ldp = *reinterpret_cast<const uint4*>(A.lead + jj - 1); g0p = A.out_off[jj - 1]; }
+        int4 first4 = make_int4(0, 0, 0, 0);
+        if (has_cur) { ldc = *reinterpret_cast<const uint4*>(A.lead + jj); g0c = A.out_off[jj]; first4 = *reinterpret_cast<const int4*>(A.ids + jj * (int64_t)W); }
+        {   // what this warp's next tile will read first: into L2 while this one is worked on
+            const int64_t jn = jj + 32 * (int64_t)nwarps;
+            if (jn < A.n_rows) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.ids + jn * (int64_t)W));
+                if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.lead + jn));
+                if ((lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.out_off + jn));
+            }
+        }
+        uint32_t run_p = 0, run_c = 0;
+        const bool pt = L != 0 && has_prev && dwj_tail_ok(ldp, W, L, &run_p);
+        const bool cf = L != 0 && has_cur && dwj_tail_ok(ldc, W, L, &run_c) && ldc.y <= (uint32_t)DWJ_LEADMAX;
+        const uint32_t slow_rows = __ballot_sync(FULL_MASK, has_cur && !cf);
+        DwjInfo me; me.base = 0; me.nrun = 0; me.nu = 0; me.a = 0; me.e = 0; me.q0 = 0;
+        if (pt || cf) {
+            uint64_t acc = 0;
+            uint32_t nb = 0, wp = 0;
+            // v: eight bytes whose first `len` (1..8) are appended; the others must be zero (forms are zero-padded in the blob)
+            auto append = [&](uint64_t v, uint32_t len) {
+                const uint32_t sh = nb * 8u;
+                acc |= v << sh;
+                const uint32_t tot = nb + len;
+                if (tot >= 8u) {
+                    *reinterpret_cast<uint64_t*>(mine + ((((wp >> 1) ^ sw) << 4) | ((wp & 1u) << 3))) = acc;
+                    wp++;
+                    acc = sh ? v >> (64u - sh) : 0ull;
+                    nb = tot - 8u;
+                } else nb = tot;
+            };
+            auto append_pad = [&](const uint8_t* p16, uint32_t cnt) {                   // cnt (1..15) bytes of the periodic text at p16
+                const uint64_t lo = *reinterpret_cast<const uint64_t*>(p16);
+                if (cnt >= 8u) {
+                    append(lo, 8u);
+                    if (cnt > 8u) append(*reinterpret_cast<const uint64_t*>(p16 + 8) & ~(~0ull << (8u * (cnt - 8u))), cnt - 8u);
+                } else append(lo & ~(~0ull << (8u * cnt)), cnt);
+            };
+            if (pt) {
+                const long long runstart = g0p + (long long)ldp.y, runend = runstart + (long long)run_p;
+                me.base = runend & ~15ll;
+                const uint32_t rt = (uint32_t)(runend & 15ll);
+                if (rt) append_pad(w.padtab + 16u * dec_mod((uint32_t)(me.base - runstart), L, w.padM), rt);   // the rest of the run of row jj - 1
+                const uint8_t* ls = T.form_blob + ldp.z;                                // its last piece (forms are padded to eight bytes in the blob)
+                for (uint32_t b = 0; b < ldp.w; b += 8) append(*reinterpret_cast<const uint64_t*>(ls + b), min(8u, ldp.w - b));
+            } else {
+                me.base = g0c & ~15ll;
+                me.a = (uint8_t)(g0c & 15ll);
+                nb = me.a & 7u; wp = me.a >> 3;
+            }
+            if (cf) {
+                const int32_t* rid = A.ids + jj * (int64_t)W;
+                const int32_t n_lead = (int32_t)ldc.x;
+                int4 nxt = first4;
+                for (int32_t i0 = 0; i0 < n_lead; i0 += 4) {
+                    const int4 v4 = nxt;
+                    if (i0 + 4 < n_lead) nxt = *reinterpret_cast<const int4*>(rid + i0 + 4);   // (W is a multiple of 4 and the rows are 16-byte aligned)
+                    const int32_t idv[4] = {v4.x, v4.y, v4.z, v4.w};
+                    uint4 ff[4];
 #pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            if (i0 + t < n_lead && fast) {
-                                const uint32_t k = min((uint32_t)idv[t], nid);                   // decoder.get(i, unk_token)
-                                const uint32_t dsc = T.mid_desc[k];
-                                const uint32_t len = dsc & 255u;
-                                if (len == 255u || pos + len > 15u + (uint32_t)DWF_LEADMAX) { fast = false; break; }
+                    for (int t = 0; t < 4; t++) ff[t] = T.mid_fast[min((uint32_t)idv[t], nid)];                // decoder.get(i, unk_token)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        if (i0 + t < n_lead) {
+                            const uint32_t len = ff[t].w >> 24;
+                            if (len <= 15u) {
+                                if (len) append((uint64_t)ff[t].x | ((uint64_t)ff[t].y << 32), min(len, 8u));
+                                if (len > 8u) append((uint64_t)ff[t].z | ((uint64_t)(ff[t].w & 0xFFFFFFu) << 32), len - 8u);
+                            } else {                                                    // a longer piece: from the blob
+                                const uint32_t dsc = T.mid_desc[min((uint32_t)idv[t], nid)], ln = dsc & 255u;   // (< 255: the lead is at most STRIDE - 72 bytes)
                                 const uint8_t* src = T.form_blob + (dsc >> 8) * 8u;
-                                for (uint32_t b = 0; b < len; b += 8) {
-                                    // eight bytes a round; what lands behind the piece's end is overwritten by the next piece (or the fill)
-                                    const uint64_t v = *reinterpret_cast<const uint64_t*>(src + b);
-                                    uint8_t* dk = sb + pos + b;
-#pragma unroll
-                                    for (int q = 0; q < 8; q++) dk[q] = (uint8_t)(v >> (8 * q));
-                                }
-                                pos += len;
+                                for (uint32_t b = 0; b < ln; b += 8) append(*reinterpret_cast<const uint64_t*>(src + b), min(8u, ln - b));
                             }
                         }
                     }
-                    if (fast && pos != a + ld.y) fast = false;                          // (cannot happen: pass 1 summed the same lengths)
-                    if (fast) {
-                        uint32_t t = 0;
-                        for (; pos & 15u; t++, pos++) sb[pos] = (uint8_t)(w.padP >> (8 * dec_mod(t, L, w.padM)));   // the run's first bytes
-                        const uint32_t nrun = (run_total - t) >> 4, done = t + (nrun << 4), rt = run_total - done;   // whole units of the run; rt < 16 bytes left
-                        for (uint32_t k = 0; k < rt; k++) sb[pos + k] = (uint8_t)(w.padP >> (8 * dec_mod(done + k, L, w.padM)));
-                        const uint8_t* lsrc = T.form_blob + ld.z;                        // the last piece behind the run
-                        for (uint32_t k = 0; k < ld.w; k++) sb[pos + rt + k] = lsrc[k];
-                        me.nl = (uint8_t)(pos >> 4); me.q0 = (uint8_t)t; me.nrun = (uint16_t)min(nrun, 65535u); me.tail = (uint8_t)(rt + ld.w); me.s_bytes = (uint16_t)pos;
-                        if (nrun > 65535u) fast = false;
-                    }
                 }
-                me.fast = fast ? 1 : 0;
+                const uint32_t pos = wp * 8u + nb, f = (0u - pos) & 15u;                // the run's first bytes, up to the next unit
+                if (f) append_pad(w.padtab, f);
+                me.q0 = (uint8_t)f;
             }
-            rowinfo[wib][lane] = me;
+            const uint32_t pos_end = wp * 8u + nb;
+            if (nb) *reinterpret_cast<uint64_t*>(mine + ((((wp >> 1) ^ sw) << 4) | ((wp & 1u) << 3))) = acc;
+            me.nu = (uint8_t)((pos_end + 15u) >> 4);
+            me.e = (uint8_t)(pos_end & 15u);                                            // (0 behind a fill)
+            me.q0 = (uint8_t)dec_mod((uint32_t)me.q0 + 512u * L - 16u * me.nu, L, w.padM);   // phase of the run's text at unit 0 of the junction
+            if (cf) {
+                const long long runend = g0c + (long long)ldc.y + (long long)run_c;
+                me.nrun = (uint32_t)(((runend & ~15ll) - (me.base + (long long)pos_end)) >> 4);
+            }
         }
+        info[wib][lane] = me;
+        const uint32_t todo = __ballot_sync(FULL_MASK, me.nu != 0 || me.nrun != 0);
         __syncwarp();
-        // ---- B. the rows, one after the other, a lane per 16-byte unit
-        uint32_t slow_rows = 0;
-        for (int j = 0; j < rows; j++) {
-            const DwfRow ri = rowinfo[wib][j];
-            if (!ri.fast) { slow_rows |= 1u << j; continue; }
-            const uint8_t* sb = leadbuf + j * DWF_STRIDE;
-            const uint32_t a = (uint32_t)(ri.g0 & 15);
-            uint8_t* const u0 = A.out + (ri.g0 - a);                                    // the first unit the row touches
-            if ((uint32_t)lane < ri.nl && (lane || !a)) __stcs(reinterpret_cast<uint4*>(u0) + lane, *reinterpret_cast<const uint4*>(sb + 16 * lane));
-            if (a && (uint32_t)lane >= a && lane < 16) u0[lane] = sb[lane];             // the unit shared with the row before: my bytes only
-            uint4* ur = reinterpret_cast<uint4*>(u0) + ri.nl;                           // the run's whole units
-            uint32_t ph = dec_mod((uint32_t)ri.q0 + 16u * (uint32_t)lane, L, w.padM);
+        // ---- B. the junctions and the runs behind them, one after the other, a lane per 16-byte unit
+        for (uint32_t rest = todo; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
+            const DwjInfo ri = info[wib][j];
+            const uint8_t* jb = jbuf + j * DWJ_STRIDE;
+            const uint32_t nu = ri.nu, nt = nu + ri.nrun, sj = (uint32_t)j & UMASK;
+            uint4* dst = reinterpret_cast<uint4*>(A.out + ri.base) + lane;
+            uint32_t ph = (uint32_t)ri.q0 + lane_ph;                                     // unit u of the run's text: phase (q0 + 16 u) mod L
+            if (ph >= L) ph -= L;
+            if ((ri.a | ri.e) == 0) {                                                   // whole units only
+                if ((uint32_t)lane < nt) __stcs(dst, *reinterpret_cast<const uint4*>((uint32_t)lane < nu ? jb + (((uint32_t)lane ^ sj) << 4) : w.padtab + 16u * ph));
+            } else if ((uint32_t)lane < nt) {
+                const uint32_t u = (uint32_t)lane;
+                const uint8_t* su = u < nu ? jb + ((u ^ sj) << 4) : w.padtab + 16u * ph;
+                const uint32_t lo = u == 0 ? ri.a : 0u, hi = (u == nu - 1 && ri.e) ? ri.e : 16u;
+                if (lo == 0 && hi == 16u) __stcs(dst, *reinterpret_cast<const uint4*>(su));
+                else for (uint32_t k = lo; k < hi; k++) reinterpret_cast<uint8_t*>(dst)[k] = su[k];
+            }
 #pragma unroll 1
-            for (uint32_t u = (uint32_t)lane; u < ri.nrun; u += 32) {
-                __stcs(ur + u, *reinterpret_cast<const uint4*>(w.padtab + 16 * ph));
+            for (uint32_t u = (uint32_t)lane + 32u; u < nt; u += 32) {                   // (a junction has at most 32 units)
                 ph += w.step; if (ph >= L) ph -= L;
+                dst += 32;
+                __stcs(dst, *reinterpret_cast<const uint4*>(w.padtab + 16u * ph));
             }
-            uint8_t* tp = reinterpret_cast<uint8_t*>(ur + ri.nrun);                     // the tail: rest of the run + the last piece
-            for (uint32_t k = (uint32_t)lane; k < ri.tail; k += 32) tp[k] = sb[ri.s_bytes + k];
         }
         __syncwarp();
-        // ---- the other rows: the general routine (its staging buffer is the lead buffer, free by now)
-        while (slow_rows) {
-            const int j = __ffs(slow_rows) - 1;
-            slow_rows &= slow_rows - 1;
-            const long long g0 = rowinfo[wib][j].g0;
-            const uint4 ld = use_lead ? *reinterpret_cast<const uint4*>(A.lead + r0 + j) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
-            const int32_t* ids = A.ids + (r0 + j) * (int64_t)W;
+        // ---- the other rows: the general routine (its staging buffer is the junction buffer, free by now)
+        for (uint32_t rest = slow_rows; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
+            const int64_t r = j0 + j;
+            const long long g0 = A.out_off[r];
+            const uint4 ld = A.lead ? *reinterpret_cast<const uint4*>(A.lead + r) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+            const int32_t* ids = A.ids + r * (int64_t)W;
             const int ne = (int32_t)ld.x >= 0 ? (int32_t)ld.x : W;
             const int32_t id_first = lane < ne ? ids[lane] : 0;
             __syncwarp();
-            dec_write_row(T, A.out, ids, W, g0, ld, id_first, wg);
+            dec_write_row(T, A.out, ids, W, g0, ld, id_first, w);
             __syncwarp();
         }
         __syncwarp();

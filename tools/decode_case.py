@@ -7,6 +7,7 @@ from genz_tokenize_b200 import Tokenize, workload
 n = 1 << 20
 dev = torch.device("cuda:0")
 tok = Tokenize(devices=[0])
+tok.set_option("max_chunk_bytes", 1 << 28)
 for kv in os.environ.get("GENZTOK_OPTIONS", "").split(","):
     if "=" in kv:
         tok.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -33,6 +34,31 @@ for W in (128, 256):
     print("W=%d ms %.3f alg GB/s %.0f text MB %.0f" % (W, ms, alg / ms / 1e6, txt.numel() / 1e6), {k: round(v["ms"] / 5, 4) for k, v in prof.items()})
     import hashlib
     print("  sha", hashlib.sha256(txt[:1 << 24].cpu().numpy().tobytes()).hexdigest()[:16], int(off[-1].item()))
+
+# sentence pairs of BASELINE configs[2] at max_len 256 (~40 ids in front of the pad run): the warp-per-row write kernel against the
+# lane-per-junction kernel with 512-byte junctions
+ta, oa, na = tok.synth_device(1234, 0, n, 0, device=dev)
+tb2, ob2, nb2 = tok.synth_device(1234, 0, n, 1, device=dev)
+outp = tok.encode_device(ta, oa, tb2, ob2, max_len=256, text_bytes=na, pair_bytes=nb2)
+torch.cuda.synchronize()
+for mode in (1, 3):
+    tok.set_option("decode_write", mode)
+    for _ in range(2):
+        txt, off = tok.decode_device(outp["input_ids"])
+    torch.cuda.synchronize()
+    tok.set_profiling(True); tok.profile_report(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in ev:
+        a.record(); txt, off = tok.decode_device(outp["input_ids"]); b.record()
+    torch.cuda.synchronize()
+    prof = tok.profile_report(reset=True)
+    tok.set_profiling(False)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / 5
+    alg = 4 * n * 256 + int(txt.numel()) + 16 * n
+    print("pairs W=256 decode_write=%d ms %.3f alg GB/s %.0f text MB %.0f" % (mode, ms, alg / ms / 1e6, txt.numel() / 1e6), {k: round(v["ms"] / 5, 4) for k, v in prof.items()})
+    print("  sha", hashlib.sha256(txt[:1 << 26].cpu().numpy().tobytes()).hexdigest()[:16], int(off[-1].item()))
+tok.set_option("decode_write", 0)
+del outp, ta, tb2, txt, off
 
 # mask-trimmed ragged rows of the same sentences (BASELINE configs[3], the other way to hand the rows over): a thread per id,
 # and the warp-per-row kernels for comparison
