@@ -583,24 +583,28 @@ def run_extras(torch, tok, S, dev, peak, workload, Tokenize):
 
     # configs[3]: decode of the encoded planes, streamed through a reused text ring
     ncd = min(len(S.calls), 8)
-    ring, dms, dbytes, rows = None, 0.0, 0, 0
-    for rep in range(2):
+    ring, dms, dms_read, dbytes, rows = None, 0.0, 0.0, 0, 0
+    for rep in range(3):                                            # 0: sizes the ring; 1: timed with the size read back per chunk; 2: timed without any host read
         for c in range(ncd):
             out = S.encode(c)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            txt, toff = tok.decode_device(out["input_ids"], out=ring)
+            txt, toff = tok.decode_device(out["input_ids"], out=ring, sync=rep < 2)
             b.record()
-            if ring is None or ring.numel() < txt.numel():
+            if rep == 0 and (ring is None or ring.numel() < txt.numel()):
                 ring = torch.empty((int(txt.numel() * 1.03) + (1 << 20),), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize()
             if rep == 1:
-                dms += a.elapsed_time(b); dbytes += int(txt.numel()); rows += out["input_ids"].shape[0]
+                dms_read += a.elapsed_time(b); dbytes += int(txt.numel()); rows += out["input_ids"].shape[0]
+            if rep == 2:
+                dms += a.elapsed_time(b)
     dalg = 4 * rows * MAX_LEN + dbytes + 16 * rows
     extra["configs3_decode_256"] = {"workload": "decode of the [chunk,256] input_ids planes of configs[2] (pads print as '<pad>'), %d chunks streamed into a reused text ring" % ncd,
                                     "rows": rows, "ms": dms, "rows_per_s": rows / (dms * 1e-3), "ids_per_s": rows * MAX_LEN / (dms * 1e-3), "text_bytes": dbytes,
                                     "alg_gb_per_s": dalg / (dms * 1e-3) / 1e9, "hbm_frac": dalg / (dms * 1e-3) / 1e9 / peak,
-                                    "note": "both passes (lengths + write) per chunk, including the device->host read of the text size between them"}
+                                    "ms_with_size_read": dms_read, "hbm_frac_with_size_read": dalg / (dms_read * 1e-3) / 1e9 / peak,
+                                    "note": "both passes (lengths + write) per chunk through genztok_decode_device_into: no host read between them (the kernels check that "
+                                            "the text fits the ring); ms_with_size_read: the same with the text size read back after every chunk"}
     del ring
     # configs[1]: 1,048,576 single sentences, max_len 128
     n1, W1 = 1 << 20, 128
@@ -618,12 +622,17 @@ def run_extras(torch, tok, S, dev, peak, workload, Tokenize):
                                      "alg_gb_per_s": alg1 / (float(np.mean(ms)) * 1e-3) / 1e9, "hbm_frac": alg1 / (float(np.mean(ms)) * 1e-3) / 1e9 / peak,
                                      "cold_ms": cold, "cold_over_warm": cold / float(np.mean(ms))}
     holder = {}
-    dms1 = float(np.mean(timed(lambda: holder.__setitem__("d", tok.decode_device(out1["input_ids"])))))
+    dms1a = float(np.mean(timed(lambda: holder.__setitem__("d", tok.decode_device(out1["input_ids"])))))
     db1 = int(holder["d"][0].numel())
+    ring1 = torch.empty((db1 + (1 << 20),), dtype=torch.uint8, device=dev)
+    dms1 = float(np.mean(timed(lambda: tok.decode_device(out1["input_ids"], out=ring1, sync=False))))
     dalg1 = 4 * n1 * W1 + db1 + 16 * n1
-    extra["configs1_decode_128"] = {"workload": "decode of the [1M,128] planes of configs[1]", "ms": dms1, "rows_per_s": n1 / (dms1 * 1e-3), "text_bytes": db1,
+    extra["configs1_decode_128"] = {"workload": "decode of the [1M,128] planes of configs[1] into a reused text buffer; L2 flushed between steps", "ms": dms1,
+                                    "rows_per_s": n1 / (dms1 * 1e-3), "text_bytes": db1,
                                     "alg_gb_per_s": dalg1 / (dms1 * 1e-3) / 1e9, "hbm_frac": dalg1 / (dms1 * 1e-3) / 1e9 / peak,
-                                    "note": "includes the allocation of the text tensor and the device->host read of its size"}
+                                    "ms_alloc_and_size_read": dms1a, "hbm_frac_alloc_and_size_read": dalg1 / (dms1a * 1e-3) / 1e9 / peak,
+                                    "note": "ms: genztok_decode_device_into, no host read; ms_alloc_and_size_read: the two-step protocol with the text tensor allocated per call"}
+    del ring1
     # the reference's DEFAULT call shape (tokenize.py:184-190: max_len=None -> no padding, no truncation): ragged rows through the
     # host API (there is no padded plane to hold them on the device); kernels by the library's CUDA events, the call by wall clock
     h1 = (t1[:b1].cpu().numpy(), o1.cpu().numpy())

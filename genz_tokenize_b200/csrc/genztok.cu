@@ -122,7 +122,7 @@ struct genztok {
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
     int64_t decode_write = 0;            // fixed-width decode, write pass: 0 = by the average lead, 1 = warp per row, 2 / 3 = lane per junction with 256 / 512 bytes (test knob)
-    int64_t decode_wide_max = 0;         // average lead (ids) up to which the 512-byte junction kernel is taken (0: never)
+    int64_t decode_wide_max = 64;        // average lead (ids) up to which the 512-byte junction kernel is taken (<= 14: never)
     int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
     int64_t copy_blocks = 64;            // blocks of k_copy_out
     int64_t copy_round = 64;             // columns the one-byte planes' copy-out is rounded up to (32 or 64: whole 64-byte lines of host memory)
@@ -1389,22 +1389,26 @@ extern "C" {
 namespace {
 
 // Both passes of the decode on one device; the caller holds h->mu (or owns the device context, as the workers of genztok_decode do).
+// capacity < 0: the two-step protocol of genztok_decode_device (d_bytes == NULL: sizes; else: the text of the same batch).
+// capacity >= 0: both steps at once into d_bytes[capacity] without a host read in between (genztok_decode_device_into).
 int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
-                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st);
+                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st, int64_t capacity = -1);
 int decode_on_device(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
-                     uint8_t* d_bytes, int64_t* total_bytes, void* stream) {
+                     uint8_t* d_bytes, int64_t* total_bytes, void* stream, int64_t capacity = -1) {
     CU(cudaSetDevice(d->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     LaunchScope::cur_stream = st;
     int rc = stream_enter(h, d, st);
     if (rc) return rc;
-    rc = decode_on_device_impl(h, d, d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, st);
+    rc = decode_on_device_impl(h, d, d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, st, capacity);
     if (rc) return rc;
     return stream_leave(h, d, st);
 }
 int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
-                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st) {
-    DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes, nullptr};
+                          uint8_t* d_bytes, int64_t* total_bytes, cudaStream_t st, int64_t capacity) {
+    const bool into = capacity >= 0 && d_bytes != nullptr;
+    if (capacity >= 0 && !into) { d_bytes = nullptr; }              // nowhere to write: sizes only
+    DecArgs A{d_ids, d_ids_off, width, n, nullptr, d_out_off, d_bytes, nullptr, nullptr, nullptr, into ? (long long)std::max<int64_t>(capacity, 1) : 0ll, 0, (int32_t)h->decode_wide_max};
     // fixed-width rows of whole 16-byte vectors whose byte counts fit 32 bits: a warp per 32 rows instead of a warp per row
     const bool fixed = !d_ids_off && width >= 4 && width % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ids) & 15) == 0 &&
                        (int64_t)width * std::max<int64_t>(1, h->H.max_form) < (1ll << 31) && h->no_fixed_decode == 0;
@@ -1426,7 +1430,7 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
         if (N < 0) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: id offsets decrease");
         if (N > (1ll << 28)) return 1;                              // too many ids for the per-id work arrays: warp per row
         CU(d->tok_flag.ensure((size_t)N + 16)); CU(d->tok_len.ensure((size_t)(N + 1) * 8)); CU(d->tok_pos.ensure((size_t)(N + 2) * 8));
-        DecTokArgs K{d_ids, d_ids_off, n, ends[0], N, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, nullptr};
+        DecTokArgs K{d_ids, d_ids_off, n, ends[0], N, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, nullptr, 0};
         CU(cudaMemsetAsync(K.flag, 0, (size_t)N + 16, st));
         { LaunchScope ls(h, d, "k_dectok_flags"); k_dectok_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(K); }
         if (N > 0) { LaunchScope ls(h, d, "k_dectok_len"); k_dectok_len<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d->T, K); }
@@ -1439,7 +1443,7 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
     };
     if (by_id) {
         int rc = GENZTOK_OK;
-        if (!d_bytes || !same_batch(1) || d->tok_n < 0) {
+        if (!d_bytes || into || !same_batch(1) || d->tok_n < 0) {
             rc = length_pass_by_id();
             if (rc < 0) return rc;
         }
@@ -1451,9 +1455,13 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
                 }
                 return GENZTOK_OK;
             }
-            DecTokArgs K{d_ids, d_ids_off, n, d->tok_base, d->tok_n, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, d_bytes};
+            DecTokArgs K{d_ids, d_ids_off, n, d->tok_base, d->tok_n, d->tok_flag.as<uint8_t>(), d->tok_len.as<int64_t>(), d->tok_pos.as<int64_t>(), d_out_off, d_bytes, A.capacity};
             if (K.n_ids > 0) { LaunchScope ls(h, d, "k_dectok_write"); k_dectok_write<<<(unsigned)((K.n_ids + 255) / 256), 256, 0, st>>>(d->T, K); }
             CU(cudaGetLastError());
+            if (into && total_bytes) {
+                CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
             return GENZTOK_OK;
         }
         d->tok_n = -1;                                              // rc == 1: fall through to the warp-per-row kernels
@@ -1463,11 +1471,18 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
         A.out_len = d->out_len.as<int64_t>();
         d->dec_avg_lead = -1;
         if (fixed) {
-            CU(d->dec_stat.ensure(16));
-            CU(cudaMemsetAsync(d->dec_stat.p, 0, 8, st));
+            CU(d->dec_stat.ensure(32));
+            CU(cudaMemsetAsync(d->dec_stat.p, 0, 16, st));
             A.lead_sum = d->dec_stat.as<unsigned long long>();
+            A.tile_ctr = d->dec_stat.as<unsigned long long>() + 1;
         }
-        if (n > 0 && fixed) { LaunchScope ls(h, d, "k_decode_len_fixed"); k_decode_len_fixed<<<grid_len, 256, 0, st>>>(d->T, A); }
+        if (n > 0 && fixed) {
+            const unsigned grid_fixed = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * DEC_LEN_MINB));
+            LaunchScope ls(h, d, "k_decode_len_fixed");
+            if (width <= 128) k_decode_len_fixed<1><<<grid_fixed, 256, 0, st>>>(d->T, A);
+            else if (width <= 256) k_decode_len_fixed<2><<<grid_fixed, 256, 0, st>>>(d->T, A);
+            else k_decode_len_fixed<0><<<grid_fixed, 256, 0, st>>>(d->T, A);
+        }
         else if (n > 0) { LaunchScope ls(h, d, "k_decode_len"); k_decode_len<<<grid_len, 256, 0, st>>>(d->T, A); }
         d->dec_sig.ids = d_ids; d->dec_sig.ids_off = d_ids_off; d->dec_sig.out_off = d_out_off; d->dec_sig.n = n; d->dec_sig.width = width; d->dec_sig.by_id = 0;
         return GENZTOK_OK;
@@ -1485,11 +1500,16 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
         return GENZTOK_OK;
     }
     // the write pass reads what the length pass of the same batch left in dec_lead; after another batch's length pass it is redone
-    if (!same_batch(0)) { int rc = length_pass(); if (rc) return rc; }
-    // Two write kernels for fixed-width rows: a lane per junction of two rows assembles short leads (single sentences, ~10 pieces in
-    // front of the pad run); the whole warp gathers long ones 32 pieces at a time (sentence pairs, ~20).  The length pass counted the pieces.
-    const int by_lanes = h->decode_write == 2 ? 1 : h->decode_write == 3 ? 2 : h->decode_write == 1 ? 0
-                         : d->dec_avg_lead < 0 ? 0 : d->dec_avg_lead <= 14.0 ? 1 : d->dec_avg_lead <= (double)h->decode_wide_max ? 2 : 0;
+    if (into) {
+        { int rc = length_pass(); if (rc) return rc; }
+        { int rc = launch_scan(h, d, st, d->out_len.as<int64_t>(), d_out_off, n); if (rc) return rc; }
+    } else if (!same_batch(0)) { int rc = length_pass(); if (rc) return rc; }
+    // Three write kernels for fixed-width rows: a lane per junction of two rows assembles short leads (single sentences, ~10 pieces in
+    // front of the pad run) in 256 bytes, longer ones in 512; the whole warp gathers the longest 32 pieces at a time.  The length pass
+    // counted the pieces.  Without a host read in between (into) all three are launched and the batch's count picks one on the device.
+    int by_lanes = h->decode_write == 2 ? 1 : h->decode_write == 3 ? 2 : h->decode_write == 1 ? 3 : 0;
+    if (by_lanes == 0 && !into) by_lanes = d->dec_avg_lead < 0 ? 3 : dec_pick((unsigned long long)(d->dec_avg_lead * (double)n + 0.5), n, (int)h->decode_wide_max);
+    A.pick = (into && fixed && by_lanes == 0) ? 1 : 0;
     auto launch_junctions = [&](auto kern, int stride, int warps) -> int {
         const size_t smem = (size_t)warps * (32 * (size_t)stride + 16);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1501,15 +1521,22 @@ int decode_on_device_impl(genztok_t* h, DeviceCtx* d, const int32_t* d_ids, cons
         kern<<<grid, warps * 32, smem, st>>>(d->T, A);
         return GENZTOK_OK;
     };
-    if (n > 0 && fixed && by_lanes == 0) {
-        LaunchScope ls(h, d, "k_decode_write_fixed");
-        k_decode_write_fixed_coop<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * 5)), 256, 0, st>>>(d->T, A);
-    } else if (n > 0 && fixed && by_lanes == 1) {
-        int rc = launch_junctions(k_decode_write_fixed<256, 8, 3>, 256, 8); if (rc) return rc;
-    } else if (n > 0 && fixed) {
-        int rc = launch_junctions(k_decode_write_fixed<512, 4, 3>, 512, 4); if (rc) return rc;
+    if (n > 0 && fixed) {
+        CU(d->dec_stat.ensure(32));
+        CU(cudaMemsetAsync(d->dec_stat.as<unsigned long long>() + 2, 0, 8, st));
+        A.tile_ctr = d->dec_stat.as<unsigned long long>() + 2;          // (one counter: only the kernel that writes takes tiles)
+        if (A.pick || by_lanes == 1) { int rc = launch_junctions(k_decode_write_fixed<256, 8, 3>, 256, 8); if (rc) return rc; }
+        if ((A.pick && h->decode_wide_max > 14) || by_lanes == 2) { int rc = launch_junctions(k_decode_write_fixed<512, 4, 3>, 512, 4); if (rc) return rc; }
+        if (A.pick || by_lanes == 3) {
+            LaunchScope ls(h, d, "k_decode_write_fixed");
+            k_decode_write_fixed_coop<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)d->sm_count * 5)), 256, 0, st>>>(d->T, A);
+        }
     }
     else if (n > 0) { LaunchScope ls(h, d, "k_decode_write"); k_decode_write<<<grid_write, 256, 0, st>>>(d->T, A); }
+    if (into && total_bytes) {
+        CU(cudaMemcpyAsync(total_bytes, d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     CU(cudaGetLastError());
     return GENZTOK_OK;
 }
@@ -1525,6 +1552,15 @@ int genztok_decode_device(genztok_t* h, int dev, const int32_t* d_ids, const int
     if (n < 0 || !d_out_off || (!d_ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device: bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     return decode_on_device(h, h->devs[(size_t)dev], d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, stream);
+}
+
+int genztok_decode_device_into(genztok_t* h, int dev, const int32_t* d_ids, const int64_t* d_ids_off, int64_t n, int32_t width, int64_t* d_out_off,
+                               uint8_t* d_bytes, int64_t capacity, int64_t* total_bytes, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n < 0 || !d_out_off || capacity < 0 || (!d_ids_off && width < 0)) return fail(h, GENZTOK_E_INVALID, "genztok_decode_device_into: bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return decode_on_device(h, h->devs[(size_t)dev], d_ids, d_ids_off, n, width, d_out_off, d_bytes, total_bytes, stream, capacity);
 }
 
 void genztok_free_text(genztok_t* h, genztok_text_t* out) {

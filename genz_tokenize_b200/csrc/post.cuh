@@ -229,6 +229,9 @@ struct DecArgs {
     uint8_t* out;
     DecLead* lead;            // written by pass 1, read by pass 2
     unsigned long long* lead_sum;   // fixed-width pass 1: ids in front of the pad runs, summed (NULL: not wanted)
+    unsigned long long* tile_ctr;   // fixed-width kernels: the next tile of 32 rows to hand out (zero at launch)
+    long long capacity;             // write pass: bytes `out` can take; a batch that needs more is not written (<= 0: not checked)
+    int32_t pick, wide_max;         // write pass, fixed-width rows: 0 = run; 1..3 = run only if the batch's average lead picks this kernel
 };
 
 __device__ __forceinline__ void dec_form(const DevTables& T, int32_t id, bool last, uint32_t* off, uint32_t* len) {
@@ -348,31 +351,52 @@ __global__ void __launch_bounds__(256, 4) k_decode_len(DevTables T, DecArgs A) {
     }
 }
 
+// Tiles of 32 rows are handed out by a counter rather than by a fixed stride: a grid of resident warps would otherwise end with
+// some warps one tile short of the others (4.6 tiles per warp on a million rows).  A warp fetches the tile after this one ahead of time.
+__device__ __forceinline__ uint64_t dec_next_tile(unsigned long long* ctr, int lane) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(ctr, 1ull);
+    return __shfl_sync(FULL_MASK, t, 0);
+}
+#ifndef DEC_LEN_MINB
+#define DEC_LEN_MINB 6
+#endif
 // Pass 1 for fixed-width rows (no offsets, width a multiple of four, ids 16-byte aligned, width x longest form < 2^31): a warp
-// takes 32 consecutive rows, reads them as a sequence of 128-id segments with four 16-byte loads in flight per lane, and keeps
-// row j's sums in lane j -- so that the per-row arithmetic (last piece, description of the pad run) and the stores are done
-// once per 32 rows, one row per lane.  The length pass is bound by instruction issue, not memory: 241 -> ~75 per 128 ids.
-__global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArgs A) {
+// takes 32 consecutive rows.
+//  A. It reads them as a sequence of 128-id segments, four 16-byte loads in flight per lane, and only LOOKS FOR THE PAD RUN: the
+//     highest index in front of the row's last id that does not hold the pad id (four compares per vector, one warp maximum per
+//     row), and the last id.  Row j's result stays in lane j.
+//  B. A lane per row then sums the form lengths of the ids in front of the run (read again: they were fetched a moment ago) --
+//     the run itself is (number of pads) x (length of the pad form) -- and writes the row's byte count and description.
+// Rows are mostly padding, so the table lookups, which bound the pass by instruction issue when done for every id (107 warp
+// instructions per row of 128 ids), are done for a tenth of them.
+template <int NSEG>   // 128-id segments per row when the width says so at compile time (1: up to 128 ids, 2: up to 256), 0: any
+__global__ void __launch_bounds__(256, DEC_LEN_MINB) k_decode_len_fixed(DevTables T, DecArgs A) {
     const int lane = threadIdx.x & 31;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int32_t pad = T.pad;
     const uint32_t nid = (uint32_t)T.n_ids;
     uint64_t padP = 0;
     const uint32_t padL = dec_pad_period(T, &padP);
+    uint32_t pad_len;                                                // bytes of the pad id's form when another piece follows
+    { const uint32_t k = min((uint32_t)pad, nid); pad_len = T.mid_desc[k] & 255u; if (pad_len == 255u) pad_len = T.mid_len[k]; }
     const int W = A.width, lim = W - 1;
-    const int nseg = (W + 127) >> 7;
+    const int nseg = NSEG ? NSEG : (W + 127) >> 7;
     const int own_lane = (lim & 127) >> 2;                           // the lane whose last vector ends with the row's last id
     const uint64_t n_tiles = ((uint64_t)A.n_rows + 31) >> 5;
     uint32_t lead_ids = 0;
-    for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
+    uint64_t tile_next = dec_next_tile(A.tile_ctr, lane);
+    for (;;) {
+        const uint64_t tile = tile_next;
+        if (tile >= n_tiles) break;
+        tile_next = dec_next_tile(A.tile_ctr, lane);
         const int64_t r0 = (int64_t)tile * 32;
         const int rows = (int)(A.n_rows - r0 < 32 ? A.n_rows - r0 : 32);
         const int32_t* p = A.ids + r0 * W;
         const int total = rows * nseg;
-        uint32_t my_run = 0; int my_hi = -1; int32_t my_idl = 0;     // lane j: row r0 + j
+        int my_hi = -1; int32_t my_idl = 0;                          // lane j: row r0 + j
         int row = 0, seg = 0;                                        // the next segment to work on
         const int32_t* q = p + 4 * lane;                             // this lane's ids of that row
-        uint32_t sum = 0; int hi = -1; int32_t lastv = 0;
+        int hi = -1; int32_t lastv = 0;
         for (int f0 = 0; f0 < total; f0 += 4) {
             int4 v[4];
             {
@@ -380,8 +404,8 @@ __global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArg
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int i0 = 128 * ls + 4 * lane;
-                    v[u] = make_int4(0, 0, 0, 0);
-                    if (f0 + u < total && i0 < W) v[u] = __ldcs(reinterpret_cast<const int4*>(lq + 128 * ls));
+                    v[u] = make_int4(pad, pad, pad, pad);
+                    if (f0 + u < total && i0 < W) v[u] = *reinterpret_cast<const int4*>(lq + 128 * ls);
                     if (++ls == nseg) { ls = 0; lq += W; }
                 }
             }
@@ -390,32 +414,46 @@ __global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArg
                 if (f0 + u < total) {
                     const int i0 = 128 * seg + 4 * lane;
                     if (i0 < W) {
-                        DEC_MID(v[u].x, i0); DEC_MID(v[u].y, i0 + 1); DEC_MID(v[u].z, i0 + 2); DEC_MID(v[u].w, i0 + 3);
+                        int h = -1;
+                        if (v[u].x != pad) h = i0;
+                        if (v[u].y != pad) h = i0 + 1;
+                        if (v[u].z != pad) h = i0 + 2;
+                        if (v[u].w != pad && i0 + 3 < lim) h = i0 + 3;       // (the row's last id is the w of its last vector: W is a multiple of four)
+                        hi = max(hi, h);
                         lastv = v[u].w;
                     }
                     if (++seg == nseg) {                             // the row is complete
-                        const uint32_t run = __reduce_add_sync(FULL_MASK, sum);
                         const int rhi = __reduce_max_sync(FULL_MASK, hi);
                         const int32_t idl = __shfl_sync(FULL_MASK, lastv, own_lane);
-                        if (lane == row) { my_run = run; my_hi = rhi; my_idl = idl; }
-                        sum = 0; hi = -1; seg = 0; row++; q += W;
+                        if (lane == row) { my_hi = rhi; my_idl = idl; }
+                        hi = -1; seg = 0; row++; q += W;
                     }
                 }
             }
         }
-        if (lane < rows) {                                           // one row per lane: the last id takes its "nothing follows" form
-            const uint32_t k = min((uint32_t)my_idl, nid);
-            uint32_t lm = T.mid_desc[k] & 255u;
-            if (lm == 255u) lm = T.mid_len[k];
-            uint32_t last_off, last_len;
-            dec_form(T, my_idl, true, &last_off, &last_len);
-            const uint32_t run = my_run - lm + last_len;
-            uint4 d = make_uint4(0xFFFFFFFFu, 0u, last_off, last_len);
-            if (padL && W >= 2 && W < DEC_MAXRUNROW) {
-                const int cnt = W - 2 - my_hi;
-                const int64_t lead_bytes = (int64_t)run - last_len - (int64_t)cnt * padL;
-                if (cnt >= DEC_MINRUN && lead_bytes >= 0) { d.x = (uint32_t)(my_hi + 1); d.y = (uint32_t)lead_bytes; }
+        if (lane < rows) {                                           // one row per lane
+            const int32_t* rid = p + (int64_t)lane * W;
+            const int n_lead = my_hi + 1;
+            uint32_t sum = 0;
+            int4 nxt = *reinterpret_cast<const int4*>(rid);
+            for (int i0 = 0; i0 < n_lead; i0 += 4) {
+                const int4 v4 = nxt;
+                if (i0 + 4 < n_lead) nxt = *reinterpret_cast<const int4*>(rid + i0 + 4);
+                const int32_t idv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t k = min((uint32_t)idv[t], nid);   // decoder.get(i, unk_token)
+                    uint32_t l = T.mid_desc[k] & 255u;
+                    if (l == 255u) l = T.mid_len[k];                 // very long vocab entry
+                    if (i0 + t < n_lead) sum += l;
+                }
             }
+            uint32_t last_off, last_len;
+            dec_form(T, my_idl, true, &last_off, &last_len);         // the last id takes its "nothing follows" form
+            const int cnt = W - 1 - n_lead;                          // pad ids in [n_lead, W - 1)
+            const uint32_t run = sum + (uint32_t)cnt * pad_len + last_len;
+            uint4 d = make_uint4(0xFFFFFFFFu, 0u, last_off, last_len);
+            if (padL && W >= 2 && W < DEC_MAXRUNROW && cnt >= DEC_MINRUN) { d.x = (uint32_t)n_lead; d.y = sum; }
             if (A.lead) *reinterpret_cast<uint4*>(A.lead + r0 + lane) = d;
             A.out_len[r0 + lane] = run;
             lead_ids += (int32_t)d.x >= 0 ? d.x : (uint32_t)W;
@@ -428,6 +466,20 @@ __global__ void __launch_bounds__(256, 4) k_decode_len_fixed(DevTables T, DecArg
 #undef DEC_MID
 
 // ---- pass 2 ----
+// The write kernel for fixed-width rows by the batch's average lead (ids in front of the pad run; the length pass summed them):
+// 1 = a lane per junction with 256 bytes (single sentences), 2 = the same with 512 bytes, 3 = the whole warp gathers 32 pieces at a time.
+__host__ __device__ inline int dec_pick(unsigned long long lead_sum, long long n_rows, int wide_max) {
+    if (lead_sum <= 14ull * (unsigned long long)n_rows) return 1;
+    if (lead_sum <= (unsigned long long)wide_max * (unsigned long long)n_rows) return 2;
+    return 3;
+}
+// Does this launch write?  Not when the text does not fit the caller's buffer (the host learns the size afterwards and calls
+// again), and not when the host launched all three kernels for fixed-width rows and the batch picks another.
+__device__ __forceinline__ bool dec_write_go(const DecArgs& A, int me) {
+    if (A.capacity > 0 && A.out_off[A.n_rows] > A.capacity) return false;
+    if (A.pick && dec_pick(*A.lead_sum, A.n_rows, A.wide_max) != me) return false;
+    return true;
+}
 struct DecWarp {              // what a warp of the write pass keeps across rows
     uint8_t* ob;              // its staging buffer (DEC_CAP + 16 bytes of shared memory)
     const uint8_t* padtab;    // [8][16]: sixteen-byte units of the periodic pad text, one per phase
@@ -565,6 +617,7 @@ __device__ __forceinline__ DecWarp dec_warp_setup(const DevTables& T, uint8_t (*
 __global__ void __launch_bounds__(256, 4) k_decode_write(DevTables T, DecArgs A) {
     __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
     __shared__ __align__(16) uint8_t padtab[8][8][16];
+    if (!dec_write_go(A, 0)) return;
     const DecWarp w = dec_warp_setup(T, stage, padtab);
     const int lane = w.lane;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -601,6 +654,7 @@ __global__ void __launch_bounds__(256, 4) k_decode_write(DevTables T, DecArgs A)
 __global__ void __launch_bounds__(256, 5) k_decode_write_fixed_coop(DevTables T, DecArgs A) {
     __shared__ __align__(16) uint8_t stage[8][DEC_CAP + 16];
     __shared__ __align__(16) uint8_t padtab[8][8][16];
+    if (!dec_write_go(A, 3)) return;
     const DecWarp w = dec_warp_setup(T, stage, padtab);
     const int lane = w.lane;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -664,19 +718,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTabl
     extern __shared__ __align__(16) uint8_t dwf_smem[];
     __shared__ __align__(16) uint8_t padtab[WARPS][8][16];
     __shared__ DwjInfo info[WARPS][32];
+    if (!dec_write_go(A, STRIDE == 256 ? 1 : 2)) return;
     const int wib = threadIdx.x >> 5;
     uint8_t* const jbuf = dwf_smem + (size_t)wib * (32 * DWJ_STRIDE + 16);             // [32][STRIDE]; the general routine's staging buffer aliases it
     DecWarp w = dec_warp_setup(T, reinterpret_cast<uint8_t (*)[DEC_CAP + 16]>(dwf_smem), padtab);
     w.ob = jbuf;
     const int lane = w.lane;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int W = A.width;
     const uint32_t L = w.padL, nid = (uint32_t)T.n_ids;
     const uint64_t n_tiles = ((uint64_t)A.n_rows + 1 + 31) >> 5;
     const uint32_t sw = (uint32_t)lane & UMASK;
     const uint32_t lane_ph = L ? dec_mod(16u * (uint32_t)lane, L, w.padM) : 0u;
     uint8_t* const mine = jbuf + lane * DWJ_STRIDE;
-    for (uint64_t tile = warp; tile < n_tiles; tile += nwarps) {
+    uint64_t tile_next = dec_next_tile(A.tile_ctr, lane);
+    for (;;) {
+        const uint64_t tile = tile_next;
+        if (tile >= n_tiles) break;
+        tile_next = dec_next_tile(A.tile_ctr, lane);
         const int64_t j0 = (int64_t)tile * 32, jj = j0 + lane;
         // ---- A. my junction: between row jj - 1 and row jj
         const bool has_prev = jj >= 1 && jj <= A.n_rows, has_cur = jj < A.n_rows;
@@ -685,8 +743,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTabl
         if (has_prev) { ldp = *reinterpret_cast<const uint4*>(A.lead + jj - 1); g0p = A.out_off[jj - 1]; }
         int4 first4 = make_int4(0, 0, 0, 0);
         if (has_cur) { ldc = *reinterpret_cast<const uint4*>(A.lead + jj); g0c = A.out_off[jj]; first4 = *reinterpret_cast<const int4*>(A.ids + jj * (int64_t)W); }
-        {   // what this warp's next tile will read first: into L2 while this one is worked on
-            const int64_t jn = jj + 32 * (int64_t)nwarps;
+        if (tile_next < n_tiles) {   // what this warp's next tile will read first: into L2 while this one is worked on
+            const int64_t jn = (int64_t)tile_next * 32 + lane;
             if (jn < A.n_rows) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(A.ids + jn * (int64_t)W));
                 if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.lead + jn));
@@ -831,6 +889,7 @@ struct DecTokArgs {
     const int64_t* pos;       // n_ids + 1: exclusive scan of len
     int64_t* out_off;         // n_rows + 1
     uint8_t* out;
+    long long capacity;       // bytes `out` can take (<= 0: not checked); a batch that needs more is not written
 };
 
 __global__ void k_dectok_flags(DecTokArgs A) {
@@ -843,6 +902,7 @@ __global__ void k_dectok_flags(DecTokArgs A) {
 __global__ void __launch_bounds__(256) k_dectok_len(DevTables T, DecTokArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_ids) return;
+    if (A.capacity > 0 && A.pos[A.n_ids] > A.capacity) return;
     uint32_t off, len;
     dec_form(T, A.ids[A.base + i], A.flag[i] != 0, &off, &len);
     A.len[i] = len;
@@ -859,6 +919,7 @@ __global__ void k_dectok_rowoff(DecTokArgs A) {
 __global__ void __launch_bounds__(256) k_dectok_write(DevTables T, DecTokArgs A) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_ids) return;
+    if (A.capacity > 0 && A.pos[A.n_ids] > A.capacity) return;
     uint32_t off, len;
     dec_form(T, A.ids[A.base + i], A.flag[i] != 0, &off, &len);
     const uint8_t* src = T.form_blob + off;

@@ -516,10 +516,12 @@ class Tokenize(object):
         import torch
         return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream or 1)
 
-    def decode_device(self, d_ids, d_ids_off=None, out=None):
+    def decode_device(self, d_ids, d_ids_off=None, out=None, sync=True):
         """Decode rows resident on the GPU: 2-D int32 tensor, or flat int32 + int64 offsets.  Returns (uint8 bytes, int64 offsets) tensors.
-        `out`: a uint8 CUDA tensor to write the text into when it is large enough (a reused ring for streamed batches); the
-        returned bytes are then a view of it."""
+        `out`: a uint8 CUDA tensor to write the text into (a reused ring for streamed batches): sizes and text are then produced
+        without a host read in between, and the returned bytes are a view of it; when the text does not fit, a tensor of the
+        right size is allocated and returned instead.  `sync=False` (with `out`) returns (out, offsets) without waiting for the
+        device: the text is out[:offsets[-1]] and nothing is written if it does not fit."""
         import torch
         dev = d_ids.device
         if d_ids_off is None:
@@ -531,11 +533,22 @@ class Tokenize(object):
         out_off = torch.empty((n + 1,), dtype=torch.int64, device=dev)
         total = C.c_int64()
         st = self._torch_stream(dev)
-        rc = self._lib.genztok_decode_device(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
-        if rc:
-            self._err(rc, "genztok_decode_device")
-        if out is None or out.numel() < max(total.value, 1) or out.device != dev or out.dtype != torch.uint8 or out.data_ptr() % 16:
-            out = torch.empty((max(total.value, 1),), dtype=torch.uint8, device=dev)
+        if out is not None and out.device == dev and out.dtype == torch.uint8 and out.data_ptr() % 16 == 0 and out.numel() > 0:
+            rc = self._lib.genztok_decode_device_into(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), out.data_ptr(), out.numel(),
+                                                      C.byref(total) if sync else None, st)
+            if rc:
+                self._err(rc, "genztok_decode_device_into")
+            if not sync:
+                return out, out_off
+            if total.value <= out.numel():
+                return out[:total.value], out_off
+        else:
+            if not sync:
+                raise ValueError("decode_device(sync=False) needs a uint8 CUDA tensor `out` (16-byte aligned) to write into")
+            rc = self._lib.genztok_decode_device(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), None, C.byref(total), st)
+            if rc:
+                self._err(rc, "genztok_decode_device")
+        out = torch.empty((max(total.value, 1),), dtype=torch.uint8, device=dev)
         rc = self._lib.genztok_decode_device(self._hd, 0, d_ids.data_ptr(), offp, n, width, out_off.data_ptr(), out.data_ptr(), None, st)
         if rc:
             self._err(rc, "genztok_decode_device")

@@ -152,6 +152,14 @@ void genztok_free_text(genztok_t *h, genztok_text_t *out);
  * the rows across them. */
 int genztok_decode_device(genztok_t *h, int dev, const int32_t *d_ids, const int64_t *d_ids_off, int64_t n,
                           int32_t width, int64_t *d_out_off, uint8_t *d_bytes, int64_t *total_bytes, void *stream);
+/* Both steps at once into a buffer the caller already has (a ring reused across streamed batches): offsets into
+ * d_out_off[n+1], text into d_bytes[capacity], no host read in between -- the kernels themselves check that the text fits
+ * and write nothing when it does not.  total_bytes == NULL: the call does not synchronise (read d_out_off[n] later);
+ * otherwise *total_bytes = bytes needed, after a synchronisation at the END of the call; when it exceeds `capacity`
+ * call again with a larger buffer.  Same rows, same text as genztok_decode_device (tokenize.py:137-139). */
+int genztok_decode_device_into(genztok_t *h, int dev, const int32_t *d_ids, const int64_t *d_ids_off, int64_t n,
+                               int32_t width, int64_t *d_out_off, uint8_t *d_bytes, int64_t capacity,
+                               int64_t *total_bytes, void *stream);
 
 /* ---- small public helpers of the class, also run on the device ------------------------------- */
 /* Tokenize.bpe(token) (tokenize.py:62-101): piece_cp[i] = code points in piece i of the word. */

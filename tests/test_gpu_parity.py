@@ -370,6 +370,49 @@ def test_decode_pad_runs(tok, oracle):
     assert tok.decode_batch(long4) == oracle.decode_batch(long4.reshape(-1), np.arange(0, 3 * 70000 + 1, 70000, dtype=np.int64))
 
 
+def test_decode_device_into_a_ring(tok, oracle):
+    # genztok_decode_device_into: sizes and text in one go into the caller's buffer, the write kernel picked on the device by the
+    # batch's average lead (all three families), the capacity checked by the kernels themselves
+    import torch
+    from genz_tokenize_b200 import Tokenize
+    rng = np.random.default_rng(91)
+    dev = torch.device("cuda:0")
+    ring = torch.empty((1 << 22,), dtype=torch.uint8, device=dev)
+    def texts(txt, off):
+        b = txt.cpu().numpy().tobytes(); o = off.cpu().numpy()
+        return [b[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
+    for width, lo, hi in [(128, 1, 14), (256, 20, 60), (256, 70, 200), (64, 1, 60), (12, 0, 3)]:   # -> 256-byte junctions, 512-byte, warp per row, mixed
+        ids = np.zeros((700, width), dtype=np.int32)
+        for r in range(700):
+            k = min(int(rng.integers(lo, hi + 1)), width)
+            ids[r, :k] = rng.integers(1, 48423, k)
+        ref = oracle.decode_batch(ids.reshape(-1), np.arange(0, 700 * width + 1, width, dtype=np.int64), threads=8)
+        d_ids = torch.from_numpy(ids).to(dev)
+        ring.fill_(255)
+        txt, off = tok.decode_device(d_ids, out=ring)
+        assert txt.data_ptr() == ring.data_ptr() and texts(txt, off) == ref, width
+        assert int(ring[txt.numel():txt.numel() + 64].min()) == 255                     # nothing behind the text
+        out2, off2 = tok.decode_device(d_ids, out=ring, sync=False)                     # no host read at all
+        torch.cuda.synchronize()
+        assert out2.data_ptr() == ring.data_ptr() and texts(out2[:int(off2[-1])], off2) == ref, width
+        small = torch.full((int(off[-1]) - 1 + 16,), 7, dtype=torch.uint8, device=dev)[:int(off[-1]) - 1]   # one byte short: nothing may be written
+        txt3, off3 = tok.decode_device(d_ids, out=small)
+        assert txt3.data_ptr() != small.data_ptr() and texts(txt3, off3) == ref and int(small.max()) == 7 and int(small.min()) == 7, width
+    # ragged rows (a thread per id) and any-width rows (a warp per row) through the same entry point
+    rows = [_pad_run_rows(rng, 1, int(w), 0, 48423, [3, 4])[0] for w in rng.integers(0, 90, 400)]
+    o = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    flat = np.concatenate(rows).astype(np.int32)
+    ref = oracle.decode_batch(flat, o, threads=8)
+    txt, off = tok.decode_device(torch.from_numpy(flat).to(dev), torch.from_numpy(o).to(dev), out=ring)
+    assert txt.data_ptr() == ring.data_ptr() and texts(txt, off) == ref
+    odd = _pad_run_rows(rng, 300, 37, 0, 48423, [3, 4])
+    txt, off = tok.decode_device(torch.from_numpy(odd).to(dev), out=ring)
+    assert texts(txt, off) == oracle.decode_batch(odd.reshape(-1), np.arange(0, 300 * 37 + 1, 37, dtype=np.int64), threads=8)
+    with pytest.raises(ValueError):
+        tok.decode_device(torch.from_numpy(odd).to(dev), sync=False)
+    assert tok.check_errors() == 0
+
+
 def test_decode_pad_runs_custom_pad_tokens():
     # pad texts of other periods: "[P] " (4 bytes, divides the unit), "\x7f" ("\x7f@@ " with the marker removed: 1 byte), "Ω" (2),
     # "a~b " (4), "ặ~ " (5), "abcdefg " (8), "abcdefgh " / "<padtok> " (9 bytes: no periodic shortcut), and strings that
