@@ -65,6 +65,7 @@ struct DeviceCtx {
     DevTables T{};
     WordCache C{};
     bool cache_ready = false;
+    bool cache_empty = true;                      // no word has been looked up since the cache was created or reset: the next text is all new
     bool force_wide = false;
     std::vector<void*> table_allocs;
     // chunk workspace
@@ -118,6 +119,7 @@ struct genztok {
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
     int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
+    int64_t no_discovery = 0;            // fused row kernel on an empty cache: do not run the byte-parallel word pass first (test knob)
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
     int64_t pad_box_cols = 0;            // columns per TMA pad box of the byte-parallel pipeline (multiple of 16; 0 = as wide as possible, up to 256)
@@ -294,6 +296,7 @@ int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     C.ctr = d->ctr.as<unsigned long long>();
     C.rank_scratch = d->rank_scratch.as<uint32_t>(); C.rank_cap = B + 64;
     d->cache_ready = true;
+    d->cache_empty = true;
     return GENZTOK_OK;
 }
 
@@ -614,8 +617,45 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         }
     }
     if (!flat) {
-        rc = launch_guard(h, d, st, bytes + 16, 0);
+        // An empty cache (first call, or after genztok_cache_reset) makes every word new.  The row kernel, a warp per long document,
+        // would walk each document until max_len WORDS -- a word not yet through BPE counts as one token -- and every row would be
+        // redone afterwards.  Instead the byte-parallel word pass of flat.cuh looks at all the text at once and fills the cache (its
+        // word arrays are not used), BPE runs, and the row kernel then finds every word.
+        const bool discover = d->cache_empty && !h->no_discovery && a.nbytes < (1ll << 31) - 65536 && (!b || b->nbytes < (1ll << 31) - 65536);
+        FlatRowsArgs F{};
+        if (discover) {
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                rc = flat_side_setup(h, d, s, s ? *b : a, s ? &a : b, n, s ? &F.b : &F.a);
+                if (rc) return rc;
+            }
+            rc = launch_guard(h, d, st, bytes + 16, 0, F.a.dsb, (uint64_t)F.a.nB * FC_OWN + 2, b ? F.b.dsb : nullptr, b ? (uint64_t)F.b.nB * FC_OWN + 2 : 0);
+        } else rc = launch_guard(h, d, st, bytes + 16, 0);
         if (rc) return rc;
+        if (discover) {
+            static const TmaPlanes no_planes{};
+            FlatWordsArgs WA{};
+            for (int s = 0; s < (b ? 2 : 1); s++) {
+                const FlatSide& S = s ? F.b : F.a;
+                { LaunchScope ls(h, d, "k_flat_doc_starts"); CU(launch_pdl(k_flat_doc_starts, dim3((unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8)), dim3(256), 0, st, d->C, S)); }
+                WA.side[s] = S;
+            }
+            const uint64_t resident = (uint64_t)d->sm_count * 3;
+            const uint64_t need_a = ((uint64_t)F.a.nB + FW_WARPS - 1) / FW_WARPS, need_b = b ? ((uint64_t)F.b.nB + FW_WARPS - 1) / FW_WARPS : 0;
+            uint64_t blocks_a = need_a, blocks_b = need_b;
+            if (need_a + need_b > resident) {
+                blocks_a = b ? std::max<uint64_t>(1, resident * need_a / (need_a + need_b)) : resident;
+                blocks_b = b ? std::max<uint64_t>(1, resident - blocks_a) : 0;
+                blocks_a = std::min(blocks_a, need_a); blocks_b = std::min(blocks_b, need_b);
+            }
+            WA.blocks_a = (uint32_t)blocks_a; WA.insert_ok = 1;
+            {
+                LaunchScope ls(h, d, "k_flat_words_discover", bytes);
+                CU(launch_pdl(k_flat_words<3, 1>, dim3((unsigned)(blocks_a + blocks_b)), dim3(FW_THREADS), 0, st, d->T, d->C, WA, no_planes));
+            }
+            CU(cudaGetLastError());
+            rc = launch_bpe(h, d, st);
+            if (rc) return rc;
+        }
         const bool tma = setup_tma(h, d, A, bytes, &M);
         rc = launch_rows<MODE_FIXED>(h, d, A, st, tma ? "k_rows_fixed_tma" : "k_rows_fixed", n, tma ? &M : nullptr);
         if (rc) return rc;
@@ -635,6 +675,7 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         k_post_rows<<<d->sm_count, 256, 0, st>>>(d->T, Q, d->C.ctr + C_FIX);
         CU(cudaGetLastError());
     }
+    d->cache_empty = false;
     return stream_leave(h, d, st);
 }
 
@@ -834,6 +875,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
     } else if (n == "no_flat") {
         h->no_flat = value;
+    } else if (n == "no_discovery") {
+        h->no_discovery = value;
     } else if (n == "flat_rows") {
         if (value < 1 || value > 32) return fail(h, GENZTOK_E_INVALID, "flat_rows must be in 1..32");
         h->flat_rows = value;
@@ -887,6 +930,7 @@ int genztok_cache_reset(genztok_t* h) {
         int rc = launch_guard(h, d, d->stream, 0, 1);
         if (rc) return rc;
         CU(cudaStreamSynchronize(d->stream));
+        d->cache_empty = true;
     }
     return GENZTOK_OK;
 }

@@ -640,6 +640,13 @@ def test_config5_custom_vocab_long_documents(oracle):
         be = tok.encode_batch(packed, pairs, max_len=4096)
         ref = orc.encode_batch(packed, pairs, max_len=4096, threads=8)
         assert_matches_oracle(be, ref, what="config5 pairs")
+        # an empty cache in front of the fused row kernel: the byte-parallel word pass fills it first (both sides); and without it
+        tok.cache_reset()
+        assert_matches_oracle(tok.encode_batch(packed, pairs, max_len=4096), ref, what="config5 pairs, empty cache")
+        tok.cache_reset()
+        tok.set_option("no_discovery", 1)
+        assert_matches_oracle(tok.encode_batch(packed, pairs, max_len=4096), ref, what="config5 pairs, empty cache, no word pass")
+        tok.set_option("no_discovery", 0)
         dec = tok.decode_batch(be["input_ids"][:8])
         assert dec == orc.decode_batch(be["input_ids"][:8].reshape(-1), np.arange(0, 8 * 4096 + 1, 4096, dtype=np.int64))
 
