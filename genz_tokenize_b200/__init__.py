@@ -8,7 +8,7 @@ generator used by the benchmark.  There is no CPU fallback.
 """
 from . import preprocess
 from .collection import DataCollection
-from .stream import iter_line_batches
+from .stream import iter_device_batches, iter_line_batches
 from .tokenizer import BatchEncoding, GenztokError, Tokenize, pack_strings
 
-__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings", "preprocess", "DataCollection", "iter_line_batches"]
+__all__ = ["Tokenize", "BatchEncoding", "GenztokError", "pack_strings", "preprocess", "DataCollection", "iter_line_batches", "iter_device_batches"]

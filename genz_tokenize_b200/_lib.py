@@ -55,6 +55,8 @@ SIGNATURES = {
     "genztok_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(Text)]),
     "genztok_free_text": (None, [C.c_void_p, C.POINTER(Text)]),
     "genztok_decode_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "genztok_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_void_p), C.c_void_p]),
     "genztok_decode_device_into": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                                              C.c_void_p]),
     "genztok_preprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Text)]),

@@ -29,6 +29,7 @@
 #include "device_common.cuh"
 #include "encode.cuh"
 #include "flat.cuh"
+#include "gather.cuh"
 #include "host_tables.hpp"
 #include "post.cuh"
 #include "prep.cuh"
@@ -1847,6 +1848,32 @@ int genztok_digest_device(genztok_t* h, int dev, const int32_t* d_ids, const uin
 /* The device pipeline counts inconsistencies (offsets outside the stated text, exhausted work lists) instead of faulting; the
  * host path checks the counter after every call, the asynchronous device path leaves that to the caller: this reads it
  * (synchronises `stream`). */
+int genztok_gather_rows(genztok_t* h, int dev, int n_fields, const void* const* d_fields, const int64_t* row_bytes, int64_t n_rows, const int64_t* d_index,
+                        int64_t n_index, void* const* d_out, void* stream) {
+    if (!h) return GENZTOK_E_INVALID;
+    if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);
+    if (n_fields < 1 || n_fields > GATHER_MAX_FIELDS || !d_fields || !row_bytes || !d_out || n_rows < 0 || n_index < 0 || (n_index > 0 && !d_index))
+        return fail(h, GENZTOK_E_INVALID, "genztok_gather_rows: bad arguments (1..%d fields)", GATHER_MAX_FIELDS);
+    GatherArgs A{};
+    for (int f = 0; f < n_fields; f++) {
+        if (!d_fields[f] || !d_out[f] || row_bytes[f] < 0 || row_bytes[f] >= (1ll << 31)) return fail(h, GENZTOK_E_INVALID, "genztok_gather_rows: field %d", f);
+        A.src[f] = static_cast<const uint8_t*>(d_fields[f]); A.dst[f] = static_cast<uint8_t*>(d_out[f]); A.row_bytes[f] = (uint32_t)row_bytes[f];
+    }
+    A.n_fields = n_fields; A.n_rows = n_rows; A.index = d_index; A.n_index = n_index;
+    if (n_index == 0) return GENZTOK_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceCtx* d = h->devs[(size_t)dev];
+    CU(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    LaunchScope::cur_stream = st;
+    {
+        LaunchScope ls(h, d, "k_gather_rows");
+        k_gather_rows<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n_index + 7) / 8, (int64_t)d->sm_count * 8)), 256, 0, st>>>(A);
+    }
+    CU(cudaGetLastError());
+    return GENZTOK_OK;
+}
+
 int genztok_check_errors(genztok_t* h, int dev, void* stream, int64_t* n_errors) {
     if (!h || !n_errors) return GENZTOK_E_INVALID;
     if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, GENZTOK_E_NODEVICE, "no such device slot %d", dev);

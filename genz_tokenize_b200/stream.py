@@ -42,3 +42,96 @@ def iter_line_batches(path, docs_per_batch=1 << 20, read_bytes=64 << 20):
                 yield buf[lo:hi], starts[b:e + 1] - lo
             if eof:
                 return
+
+
+def iter_device_batches(path, docs_per_batch=1 << 20, read_bytes=64 << 20, device=None, depth=2):
+    """`iter_line_batches` delivered on the GPU, with the three stages overlapped: a reader thread reads the file and scans it for
+    line ends into pinned staging buffers (`depth` slots), the host->device copies run on their own CUDA stream, and the consumer
+    -- which tokenises batch i on its stream meanwhile -- only waits on the copy's event.  Yields
+    `(d_bytes uint8, d_off int64[n+1], nbytes)`: `d_bytes` is padded so that the kernels' 16-byte loads stay inside it
+    (`Tokenize.encode_device(d_bytes, d_off, ..., text_bytes=nbytes)`).  The tensors of a batch belong to its slot: they are
+    valid until the generator is asked for the next batch (with `depth` > 2: for `depth - 2` more batches)."""
+    import queue
+    import threading
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    depth = max(2, int(depth))
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    class Slot:
+        def __init__(self):
+            self.h_bytes = self.h_off = self.d_bytes = self.d_off = None
+            self.copied = torch.cuda.Event()           # recorded on the copy stream: the batch is on the device
+            self.released = None                       # recorded on the consumer's stream when it is done with the slot
+
+        def fit(self, nb, no):
+            if self.h_bytes is None or self.h_bytes.numel() < nb:
+                cap = int(nb * 1.25) + 4096
+                self.h_bytes = torch.empty((cap,), dtype=torch.uint8, pin_memory=True)
+                self.d_bytes = torch.empty((cap,), dtype=torch.uint8, device=dev)
+            if self.h_off is None or self.h_off.numel() < no:
+                cap = int(no * 1.25) + 16
+                self.h_off = torch.empty((cap,), dtype=torch.int64, pin_memory=True)
+                self.d_off = torch.empty((cap,), dtype=torch.int64, device=dev)
+
+    free, ready = queue.Queue(), queue.Queue(maxsize=depth)
+    for _ in range(depth):
+        free.put(Slot())
+    stop = threading.Event()
+
+    def reader():
+        try:
+            torch.cuda.set_device(dev)
+            for b, o in iter_line_batches(path, docs_per_batch, read_bytes):
+                slot = free.get()
+                if stop.is_set():
+                    return
+                nb, no = len(b), len(o)
+                pad = nb + (-nb) % 16 + 32
+                slot.fit(pad, no)
+                hb = slot.h_bytes.numpy()
+                hb[:nb] = b
+                hb[nb:pad] = 0
+                slot.h_off.numpy()[:no] = o
+                with torch.cuda.stream(copy_stream):
+                    if slot.released is not None:
+                        copy_stream.wait_event(slot.released)          # the consumer's kernels on the slot's old contents
+                    slot.d_bytes[:pad].copy_(slot.h_bytes[:pad], non_blocking=True)
+                    slot.d_off[:no].copy_(slot.h_off[:no], non_blocking=True)
+                    slot.copied.record(copy_stream)
+                ready.put((slot, nb, pad, no))
+            ready.put(None)
+        except BaseException as e:                                    # hand the failure to the consumer
+            ready.put(e)
+
+    th = threading.Thread(target=reader, name="genztok-line-reader", daemon=True)
+    th.start()
+    held = []
+    try:
+        while True:
+            item = ready.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            slot, nb, pad, no = item
+            torch.cuda.current_stream(dev).wait_event(slot.copied)
+            held.append(slot)
+            yield slot.d_bytes[:pad], slot.d_off[:no], nb
+            # the consumer is back: what it launched on the oldest slot is in its stream by now -> the reader may refill it
+            while len(held) >= depth - 1 and held:
+                s = held.pop(0)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                s.released = ev
+                free.put(s)
+    finally:
+        stop.set()
+        while not ready.empty():                                      # a reader blocked on a full queue
+            try:
+                ready.get_nowait()
+            except queue.Empty:
+                break
+        for _ in range(depth):
+            free.put(Slot.__new__(Slot))                             # wake the reader if it waits for a slot
+        th.join(timeout=5)

@@ -210,6 +210,16 @@ int genztok_set_option(genztok_t *h, const char *name, int64_t value);
  * *n_errors = inconsistencies counted since the handle was created; returns GENZTOK_E_CUDA when it is not zero. */
 int genztok_check_errors(genztok_t *h, int dev, void *stream, int64_t *n_errors);
 
+/* ---- the step behind the tokenizer ----------------------------------------------------------------
+ * DataCollection.to_tf_dataset (genz_tokenize/models/bert/dataset.py:28-55) shuffles the whole collection and cuts it into
+ * batches of ({field: rows}, y).  For fields that stay on the device one launch gathers a batch of every field:
+ * d_out[f][i, :] = d_fields[f][d_index[i], :] for f < n_fields (<= GENZTOK_MAX_FIELDS), row_bytes[f] bytes per row of field f,
+ * n_rows rows per field, d_index[n_index] on the device (a number outside [0, n_rows) gives a row of zero bytes).  Does not
+ * synchronise. */
+#define GENZTOK_MAX_FIELDS 8
+int genztok_gather_rows(genztok_t *h, int dev, int n_fields, const void *const *d_fields, const int64_t *row_bytes,
+                        int64_t n_rows, const int64_t *d_index, int64_t n_index, void *const *d_out, void *stream);
+
 /* ---- measurement plumbing (not part of the reference's surface; used by bench.py and the tests) ------------------- */
 /* The synthetic workload of SURVEY.md 8 d2 produced on the device: the counter-based generator that
  * genz_tokenize_b200/workload.py::generate_hashed defines (same bytes).  genztok_synth_init uploads the word list

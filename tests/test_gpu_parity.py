@@ -557,6 +557,36 @@ def test_file_to_device_batches_handoff(tok, oracle):
         assert feats["input_ids"].is_cuda and feats["attention_mask"].is_cuda and yy.is_cuda
         got[yy] = feats["input_ids"]
     assert np.array_equal(got.cpu().numpy(), ids)
+    # the batches are cut by the library's gather kernel, one launch for all the fields of a batch (rows of whole 16-byte
+    # vectors, an int8 plane of odd width, 8-byte labels): every field equals index_select with the same permutation
+    n0 = tok.launch_count()
+    odd = torch.arange(3000 * 7, device=dev, dtype=torch.int32).reshape(3000, 7).to(torch.int8)
+    dc2 = DataCollection(input_ids=out["input_ids"], attention_mask=out["attention_mask"], token_type_ids=odd, y=y)
+    g = torch.Generator(device="cpu"); g.manual_seed(9)
+    order = torch.randperm(3000, generator=g).to(dev)
+    nb = 0
+    for i, (feats, yy) in enumerate(dc2.to_torch_batches(batch_size=700, seed=9, tokenizer=tok)):
+        idx = order[700 * i:700 * (i + 1)]
+        assert torch.equal(yy, y[idx]) and torch.equal(feats["input_ids"], out["input_ids"][idx])
+        assert torch.equal(feats["attention_mask"], out["attention_mask"][idx]) and torch.equal(feats["token_type_ids"], odd[idx])
+        nb += 1
+    assert nb == 5 and tok.launch_count() - n0 == 5
+    assert [yy.tolist() for _, yy in DataCollection(input_ids=out["input_ids"], y=y).to_torch_batches(batch_size=1500, shuffle=False)] == [list(range(1500)), list(range(1500, 3000))]
+    # the reader with the file read, the line scan and the host->device copy of the next batch overlapped with this batch's kernels
+    from genz_tokenize_b200 import iter_device_batches
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "docs.txt")
+        open(p, "wb").write(("\n".join(lines) + "\n").encode("utf-8"))
+        host = list(iter_line_batches(p, docs_per_batch=700, read_bytes=30000))
+        rows, k = [], 0
+        for d_b, d_o, nbytes in iter_device_batches(p, docs_per_batch=700, read_bytes=30000, device=dev):
+            hb, ho = host[k]; k += 1
+            assert nbytes == len(hb) and d_b.numel() % 16 == 0 and np.array_equal(d_b[:nbytes].cpu().numpy(), hb) and np.array_equal(d_o.cpu().numpy(), ho)
+            rows.append(tok.encode_device(d_b, d_o, max_len=32, text_bytes=nbytes)["input_ids"])
+        assert k == len(host)
+        assert np.array_equal(torch.cat(rows).cpu().numpy(), ids)
+        it = iter_device_batches(p, docs_per_batch=100, device=dev)       # a consumer that stops early leaves no reader behind
+        next(it); it.close()
 
 
 def test_config2_full_size_properties(tok, oracle):
