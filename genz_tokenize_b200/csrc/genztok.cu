@@ -727,6 +727,7 @@ struct PinnedVec {
         n = m;
         return true;
     }
+    bool reserve(size_t m) { const size_t keep = n; if (m * sizeof(T) > cap_bytes) { if (!resize(m)) return false; n = keep; } return true; }
     T* data() { return p; }
     size_t size() const { return n; }
     bool empty() const { return n == 0; }
@@ -1024,8 +1025,9 @@ struct EncodePart {
     int32_t extent = 0;            // fixed layout: columns that can differ from padding, max over this part's chunks
     int64_t d2h_bytes = 0;
     PinnedVec<int32_t> ids, spans; PinnedVec<uint8_t> mask; PinnedVec<int8_t> tt, seq;
+    PinnedVec<int64_t> offs, soffs;   // a chunk's row / span offsets on their way home (pinned: a copy into pageable memory is staged by the driver)
     int64_t total = 0, span_total = 0, tokens = 0;
-    void bind(genztok_t* h) { ids.h = h; spans.h = h; mask.h = h; tt.h = h; seq.h = h; }
+    void bind(genztok_t* h) { ids.h = h; spans.h = h; mask.h = h; tt.h = h; seq.h = h; offs.h = h; soffs.h = h; }
 };
 
 void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64_t rb, int64_t re, EncodePart* part) {
@@ -1249,10 +1251,17 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
         CUF(cudaGetLastError());
         // bring the chunk home; offsets are kept relative to this device's part
         const size_t old = part->ids.size();
+        if (old == 0 && r1 < re) {                                  // first chunk of several: room for the whole part at this chunk's tokens per row (+ 12 %)
+            const size_t est = (size_t)((double)total * (double)(re - rb) / (double)m * 1.125) + 4096;
+            bool ok = part->ids.reserve(est) && part->mask.reserve(est);
+            if (has_pair) ok = ok && part->tt.reserve(est) && part->seq.reserve(est);
+            if (!ok) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
+        }
         bool grown = part->ids.resize(old + (size_t)total) && part->mask.resize(old + (size_t)total);
         if (has_pair) grown = grown && part->tt.resize(old + (size_t)total) && part->seq.resize(old + (size_t)total);
+        grown = grown && part->offs.resize((size_t)m + 1);
         if (!grown) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
-        std::vector<int64_t> offs((size_t)m + 1);
+        int64_t* const offs = part->offs.data();
         if (total) {
             CUF(cudaMemcpyAsync(part->ids.data() + old, d->ids.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
             CUF(cudaMemcpyAsync(part->mask.data() + old, d->mask.p, (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -1261,15 +1270,17 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
                 CUF(cudaMemcpyAsync(part->seq.data() + old, d->seq.p, (size_t)total, cudaMemcpyDeviceToHost, st));
             }
         }
-        std::vector<int64_t> soffs;
+        int64_t* soffs = nullptr;
         if (want_spans) {
-            soffs.resize((size_t)m + 1);
+            if (!part->soffs.resize((size_t)m + 1)) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
+            soffs = part->soffs.data();
             const size_t so = part->spans.size();
+            if (so == 0 && r1 < re && !part->spans.reserve((size_t)((double)span_n * 2.0 * (double)(re - rb) / (double)m * 1.125) + 4096)) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
             if (!part->spans.resize(so + (size_t)span_n * 2)) PFAIL(GENZTOK_E_NOMEM, "pinned host allocation failed")
             if (span_n) CUF(cudaMemcpyAsync(part->spans.data() + so, d->spans.p, (size_t)span_n * 8, cudaMemcpyDeviceToHost, st));
-            CUF(cudaMemcpyAsync(soffs.data(), d->span_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CUF(cudaMemcpyAsync(soffs, d->span_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
-        CUF(cudaMemcpyAsync(offs.data(), d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUF(cudaMemcpyAsync(offs, d->row_off.p, (size_t)(m + 1) * 8, cudaMemcpyDeviceToHost, st));
         CUF(cudaMemcpyAsync(out->row_len + r0, d->row_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
         if (has_pair) {
             CUF(cudaMemcpyAsync(out->seq_len + r0, d->seq_len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
@@ -1277,9 +1288,10 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
             CUF(cudaMemcpyAsync(out->row_status + r0, d->status.p, (size_t)m, cudaMemcpyDeviceToHost, st));
         }
         CUF(cudaStreamSynchronize(st));
-        for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = part->total + offs[(size_t)i];      // relative to the part
+        part->d2h_bytes += total * (has_pair ? 7 : 5) + (m + 1) * 8 + m * (has_pair ? 13 : 4) + (want_spans ? span_n * 8 + (m + 1) * 8 : 0);
+        for (int64_t i = 1; i <= m; i++) out->row_off[r0 + i] = part->total + offs[i];      // relative to the part
         part->total += total;
-        if (want_spans) { for (int64_t i = 1; i <= m; i++) out->span_off[r0 + i] = part->span_total + soffs[(size_t)i]; part->span_total += span_n; }
+        if (want_spans) { for (int64_t i = 1; i <= m; i++) out->span_off[r0 + i] = part->span_total + soffs[i]; part->span_total += span_n; }
     }
     unsigned long long tokens_after = 0, nerr = 0;
     CUF(cudaMemcpyAsync(&tokens_after, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
@@ -1396,7 +1408,26 @@ int genztok_encode(genztok_t* h, const uint8_t* text, const int64_t* text_off, c
         // stitch the parts: shift every part's row offsets by what came before it, concatenate the flat planes
         int64_t base = 0, sbase = 0;
         size_t ntot = 0, stot = 0;
-        for (auto& pt : parts) { ntot += pt.ids.size(); stot += pt.spans.size(); }
+        int holders = 0;
+        for (auto& pt : parts) { ntot += pt.ids.size(); stot += pt.spans.size(); holders += (pt.ids.size() || pt.spans.size()) ? 1 : 0; }
+        if (holders == 1) {
+            // one device holds the whole result: its pinned buffers become the caller's (no second copy); they return to the pool on free
+            for (auto& pt : parts) {
+                if (!(pt.ids.size() || pt.spans.size())) continue;
+                auto adopt = [&](auto& v) { auto* q = v.p; if (q) { ob->pinned.push_back({q, v.cap_bytes}); v.p = nullptr; v.cap_bytes = 0; v.n = 0; } return q; };
+                out->total = pt.total;
+                out->input_ids = adopt(pt.ids); out->attention_mask = adopt(pt.mask);
+                if (has_pair) { out->token_type_ids = adopt(pt.tt); out->sequence_id = adopt(pt.seq); }
+                if (J.want_spans) out->spans = adopt(pt.spans);
+            }
+            auto some = [&](size_t bytes) { void* q = malloc(bytes); ob->mallocs.push_back(q); return q; };   // (empty planes still get an address)
+            if (!out->input_ids) out->input_ids = (int32_t*)some(16);
+            if (!out->attention_mask) out->attention_mask = (uint8_t*)some(16);
+            if (has_pair && !out->token_type_ids) out->token_type_ids = (int8_t*)some(16);
+            if (has_pair && !out->sequence_id) out->sequence_id = (int8_t*)some(16);
+            if (J.want_spans && !out->spans) out->spans = (int32_t*)some(16);
+            return GENZTOK_OK;
+        }
         int32_t* ids = (int32_t*)malloc(std::max<size_t>(ntot * 4, 16)); ob->mallocs.push_back(ids);
         uint8_t* mask = (uint8_t*)malloc(std::max<size_t>(ntot, 16)); ob->mallocs.push_back(mask);
         int8_t *tt = nullptr, *seq = nullptr; int32_t* spans = nullptr;
