@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTabl
     const int W = A.width;
     const uint32_t L = w.padL, nid = (uint32_t)T.n_ids;
     const uint64_t n_tiles = ((uint64_t)A.n_rows + 1 + 31) >> 5;
-    const uint32_t sw = (uint32_t)lane & UMASK;
+    const uint32_t sw2 = ((uint32_t)lane & UMASK) << 1;              // word wp of my junction lives in unit (wp >> 1) ^ (lane & UMASK): (wp ^ sw2) is its 8-byte word
     const uint32_t lane_ph = L ? dec_mod(16u * (uint32_t)lane, L, w.padM) : 0u;
     uint8_t* const mine = jbuf + lane * DWJ_STRIDE;
     uint64_t tile_next = dec_next_tile(A.tile_ctr, lane);
@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTabl
                 acc |= v << sh;
                 const uint32_t tot = nb + len;
                 if (tot >= 8u) {
-                    *reinterpret_cast<uint64_t*>(mine + ((((wp >> 1) ^ sw) << 4) | ((wp & 1u) << 3))) = acc;
+                    *reinterpret_cast<uint64_t*>(mine + ((wp ^ sw2) << 3)) = acc;
                     wp++;
                     acc = sh ? v >> (64u - sh) : 0ull;
                     nb = tot - 8u;
@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_decode_write_fixed(DevTabl
                 me.q0 = (uint8_t)f;
             }
             const uint32_t pos_end = wp * 8u + nb;
-            if (nb) *reinterpret_cast<uint64_t*>(mine + ((((wp >> 1) ^ sw) << 4) | ((wp & 1u) << 3))) = acc;
+            if (nb) *reinterpret_cast<uint64_t*>(mine + ((wp ^ sw2) << 3)) = acc;
             me.nu = (uint8_t)((pos_end + 15u) >> 4);
             me.e = (uint8_t)(pos_end & 15u);                                            // (0 behind a fill)
             me.q0 = (uint8_t)dec_mod((uint32_t)me.q0 + 512u * L - 16u * me.nu, L, w.padM);   // phase of the run's text at unit 0 of the junction
