@@ -660,6 +660,19 @@ def run_extras(torch, tok, S, dev, peak, workload, Tokenize):
                                     "tokens_per_s_call": rtok / (call_ms * 1e-3), "alg_gb_per_s_kernels": ralg / (rk_ms * 1e-3) / 1e9,
                                     "hbm_frac_kernels": ralg / (rk_ms * 1e-3) / 1e9 / peak, "h2d_bytes": int(b1 + 8 * (n1 + 1)), "d2h_bytes": rd2h,
                                     "kernels": {k: round(v["ms"], 4) for k, v in rprof.items() if v["ms"] > 0.005}}
+    # configs[1] end to end through the host API: the same sentences, max_len=128, pinned text in, pinned planes out
+    tok.encode_batch(h1, max_len=W1)                                # allocations
+    calls1 = []
+    for _ in range(5):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        be1 = tok.encode_batch(h1, max_len=W1)
+        calls1.append((time.perf_counter() - t0) * 1e3)
+        e_tok, e_d2h = int(be1["real_tokens"]), int(be1.d2h_bytes); del be1
+    c1 = float(np.median(calls1))
+    extra["configs1_e2e_host"] = {"workload": "the 1,048,576 single sentences, max_len=128, Tokenize.encode_batch: pinned host text in, pinned [n,128] planes out "
+                                              "(only the columns that can differ from padding cross PCIe)",
+                                  "call_ms": c1, "call_ms_all": [round(c, 2) for c in calls1], "tokens_per_s": e_tok / (c1 * 1e-3),
+                                  "h2d_bytes": int(b1 + 8 * (n1 + 1)), "d2h_bytes": e_d2h, "d2h_gb_per_s": e_d2h / (c1 * 1e-3) / 1e9}
     del ht1, h1
     L.load().genztok_host_free(hp1)
     del rg, t1, o1, holder
