@@ -782,6 +782,24 @@ def test_config3_full_chunk_vs_oracle(oracle, doc0):
     assert np.array_equal(tt.reshape(-1).astype(np.int32), ref["tt"])
     assert np.array_equal(out["seq_len"].cpu().numpy(), np.diff(ref["seq_off"]))
     assert np.array_equal(out["row_len"].cpu().numpy().astype(np.int64), ref["mask"].reshape(n, W).sum(axis=1))
+    if doc0 == 0:
+        # BASELINE configs[3] at full size: the chunk's [1,048,576 x 256] ids decoded on the device in one go (sizes + text into a
+        # ring, the write kernel picked on the device, 32,769 tiles of junctions handed out by the counter); three slices of 65,536
+        # rows -- the first, one from the middle that starts inside a tile, the last -- against the oracle, byte for byte
+        ring = torch.empty((1 << 31,), dtype=torch.uint8, device=dev)
+        txt, off = tok.decode_device(out["input_ids"], out=ring)
+        assert txt.data_ptr() == ring.data_ptr() and tok.check_errors(dev) == 0
+        ho = off.cpu().numpy()
+        assert ho[0] == 0 and ho[-1] == txt.numel() and (np.diff(ho) > 0).all()
+        ids = ref["ids"].reshape(n, W)
+        for lo in (0, 524288 + 13, n - 65536):
+            hi = lo + 65536
+            want = oracle.decode_batch(ids[lo:hi].reshape(-1), np.arange(0, 65536 * W + 1, W, dtype=np.int64), threads=max(Oracle.max_threads(), os.cpu_count() or 1))
+            blob = txt[int(ho[lo]):int(ho[hi])].cpu().numpy().tobytes()
+            rel = ho[lo:hi + 1] - ho[lo]
+            assert [blob[rel[i]:rel[i + 1]].decode("utf-8") for i in range(65536)] == want, lo
+        txt2, off2 = tok.decode_device(out["input_ids"])             # the two-step protocol gives the same bytes
+        assert torch.equal(off2, off) and torch.equal(txt2, txt)
 
 
 def test_cuda_path_against_the_reference_itself(tok):
