@@ -46,7 +46,7 @@ static const uint32_t SLOT_LOCKED = 0xFFFFFFFFu;
 static const uint32_t KEY_INLINE = 24;
 static const uint32_t VAL_PENDING = 0u, VAL_SINGLE = 1u << 30, VAL_MULTI = 2u << 30, VAL_KIND = 3u << 30, VAL_PAYLOAD = (1u << 30) - 1;
 
-enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_FLATFIX_A = 9, C_FLATFIX_B = 10, C_SCRATCH = 11, C_TICKET = 12, C_COUNT = 16 };
+enum Counter { C_SLOTS = 0, C_KEYS = 1, C_TOKS = 2, C_PENDING = 3, C_REDO = 4, C_FIX = 5, C_RESET = 6, C_ERR = 7, C_TOKENS = 8, C_FLATFIX_A = 9, C_FLATFIX_B = 10, C_SCRATCH = 11, C_TICKET = 12, C_OVER32 = 13, C_COUNT = 16 };
 
 struct WordCache {
     Slot* slots;

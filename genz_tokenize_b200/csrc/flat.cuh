@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
     const uint32_t n_tiles = (uint32_t)((A.n_rows + D - 1) / D);
     const uint32_t n_warps = gridDim.x * (uint32_t)wpb;
     const uint4 pad4 = make_uint4((uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad, (uint32_t)T.pad);
-    uint32_t tok_total = 0;
+    uint32_t tok_total = 0; uint32_t over32 = 0;
     const uint64_t l2_first = l2_policy_evict_first();
     // Two loads head a tile's chain of dependent loads: the document offsets of my row, then the start bits / prefix of the
     // two granules they point into.  Both are issued ahead: the offsets two tiles ahead, the rank data one tile ahead.
@@ -840,6 +840,7 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
         if (lane < nd) {
             const uint4 fc = ts->fc[lane];
             const int32_t dL = (int32_t)fc.x, m = (int32_t)fc.z;
+            if (dL > 32 || (pair && m > 32)) over32++;               // (the host stages 32 columns next time when hardly any row needs more)
             const bool again = (fc.w & FF_AGAIN) || (KR < W && (dL > KR || (pair && m > KR)));
             if (again) {
                 const unsigned long long k = atomicAdd(&C.ctr[C_REDO], 1ULL);
@@ -861,6 +862,8 @@ __global__ void __launch_bounds__(256, MINB) k_flat_rows(DevTables T, WordCache 
     __syncwarp();
     tok_total = __reduce_add_sync(FULL_MASK, tok_total);
     if (lane == 0 && tok_total) atomicAdd(&C.ctr[C_TOKENS], (unsigned long long)tok_total);
+    over32 = __reduce_add_sync(FULL_MASK, over32);
+    if (lane == 0 && over32) atomicAdd(&C.ctr[C_OVER32], (unsigned long long)over32);
 }
 
 }  // namespace gzt

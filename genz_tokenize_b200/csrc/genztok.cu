@@ -89,6 +89,12 @@ struct DeviceCtx {
     } stage[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int32_t* h_extent = nullptr;                  // pinned: [2] staged-column extents of the two chunks in flight
+    // byte-parallel pipeline: rows of more than 32 tokens in the last sampled call (k_flat_rows counts them; read back without a
+    // synchronisation).  When hardly any row needs more, the next call stages 32 columns instead of 64 and leaves the rest to the pad boxes.
+    unsigned long long* h_over32 = nullptr;       // pinned
+    cudaEvent_t over32_ev = nullptr;
+    bool over32_pending = false, stage32 = false;
+    int64_t over32_rows = 0;
     // the shared work areas (word cache, lists, flat arrays) are used by one stream at a time: a call on another stream
     // first waits for the event the previous call left behind
     cudaEvent_t last_done = nullptr;
@@ -120,6 +126,7 @@ struct genztok {
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
     int64_t grid_mult = 1;               // row-kernel grid = resident blocks x grid_mult
     int64_t no_flat = 0;                 // use the fused row kernel even where the byte-parallel pipeline applies (test knob)
+    int64_t no_stage32 = 0;              // byte-parallel pipeline: never narrow the staged columns to 32 by the previous call's row lengths (test knob)
     int64_t no_discovery = 0;            // fused row kernel on an empty cache: do not run the byte-parallel word pass first (test knob)
     int64_t flat_rows = 32;              // rows per warp tile of k_flat_rows
     int64_t no_side_pads = 0;            // k_flat_rows writes the pad columns itself (test knob)
@@ -517,7 +524,16 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     if (flat) {
         RowArgs Af = A;
         Af.D = (int32_t)h->flat_rows;
+        if (d->over32_pending && cudaEventQuery(d->over32_ev) == cudaSuccess) {
+            d->stage32 = d->h_over32[0] * 1000ull <= (unsigned long long)d->over32_rows;      // at most 0.1 % of the rows would take the second pass
+            d->over32_pending = false;
+        }
+        cudaGetLastError();                                           // (cudaErrorNotReady of the query is not an error)
+        const int64_t kr_auto = std::max<int64_t>(32, (bytes / n / 3 + 12 + (b ? 4 : 0) + 15) & ~15ll);
+        const bool narrow = !h->force_kr && !h->no_stage32 && d->stage32 && kr_auto == 64 && W >= 96;
+        if (narrow) h->force_kr = 32;
         flat = setup_tma(h, d, Af, bytes, &M, sizeof(FlatTile));
+        if (narrow) h->force_kr = 0;
         if (flat) {
             FlatRowsArgs F{};
             for (int s = 0; s < (b ? 2 : 1); s++) {
@@ -615,6 +631,13 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
                 CU(launch_pdl(kern, dim3((unsigned)blocks), dim3(256), smem, st, d->T, d->C, F, M));
             }
             CU(cudaGetLastError());
+            if (!d->over32_pending && n >= 4096) {                    // sample this call's count of rows longer than 32 tokens
+                if (!d->h_over32) CU(cudaHostAlloc(reinterpret_cast<void**>(&d->h_over32), 64, cudaHostAllocDefault));
+                if (!d->over32_ev) CU(cudaEventCreateWithFlags(&d->over32_ev, cudaEventDisableTiming));
+                CU(cudaMemcpyAsync(d->h_over32, d->C.ctr + C_OVER32, 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaEventRecord(d->over32_ev, st));
+                d->over32_pending = true; d->over32_rows = n;
+            }
         }
     }
     if (!flat) {
@@ -803,6 +826,8 @@ void genztok_destroy(genztok_t* h) {
         if (d->s_in) cudaStreamDestroy(d->s_in);
         if (d->s_out) cudaStreamDestroy(d->s_out);
         if (d->h_extent) cudaFreeHost(d->h_extent);
+        if (d->h_over32) cudaFreeHost(d->h_over32);
+        if (d->over32_ev) cudaEventDestroy(d->over32_ev);
         if (d->last_done) cudaEventDestroy(d->last_done);
         d->synth_len.release();
         for (auto& fb : d->flat) for (DevBuf* b : {&fb.dsb, &fb.st, &fb.tpref, &fb.cnt, &fb.wtok}) b->release();
@@ -877,6 +902,8 @@ int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
         for (DeviceCtx* d : h->devs) d->force_wide = value != 0;
     } else if (n == "no_flat") {
         h->no_flat = value;
+    } else if (n == "no_stage32") {
+        h->no_stage32 = value;
     } else if (n == "no_discovery") {
         h->no_discovery = value;
     } else if (n == "flat_rows") {

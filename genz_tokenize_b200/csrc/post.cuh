@@ -977,7 +977,7 @@ __global__ void k_cache_guard(WordCache C, unsigned long long need_slots, unsign
     const bool reset = force || (c[C_SLOTS] + need_slots) * 2 > cap || c[C_KEYS] + need_keys > C.key_cap || c[C_TOKS] + need_toks > C.tok_cap;
     c[C_RESET] = reset;
     if (reset) { c[C_SLOTS] = 0; c[C_KEYS] = 0; c[C_TOKS] = 0; }
-    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0; c[C_SCRATCH] = 0; c[C_TICKET] = 0;
+    c[C_PENDING] = 0; c[C_REDO] = 0; c[C_FIX] = 0; c[C_FLATFIX_A] = 0; c[C_FLATFIX_B] = 0; c[C_SCRATCH] = 0; c[C_TICKET] = 0; c[C_OVER32] = 0;
 }
 // ... and two optional word arrays to zero on the way (the document-start bitmaps of the byte-parallel pipeline)
 __global__ void k_cache_clear(WordCache C, uint32_t* z0, uint64_t n0, uint32_t* z1, uint64_t n1) {
