@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(256) k_bpe_pending(DevTables T, WordCache C) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint64_t npend = C.ctr[C_PENDING];
     if (npend > C.pending_cap) npend = C.pending_cap;
+    // no more warps than words draw tickets (in steady state nothing is pending: thousands of warps would queue up on one atomic)
+    if ((((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) >= npend) return;
     // words are handed out by a ticket: a 1,200-byte token costs a thousand times a syllable, a fixed assignment of words to
     // warps would leave the kernel waiting for the warp that drew several of them
     for (;;) {

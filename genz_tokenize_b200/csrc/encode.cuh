@@ -657,6 +657,7 @@ __device__ __forceinline__ void walk_side(const DevTables& T, const WordCache& C
 template <int MODE, typename TokT, bool TMA>
 __global__ void __launch_bounds__(256, 4) k_rows(DevTables T, WordCache C, RowArgs A, const __grid_constant__ TmaPlanes M) {
     pdl_wait(); pdl_trigger();
+    if (A.row_list && C.ctr[C_REDO] == 0) return;                   // second pass with nothing to redo (the usual case): before any set-up
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int32_t W = A.W, D = A.D;

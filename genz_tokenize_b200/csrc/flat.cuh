@@ -124,12 +124,16 @@ __device__ __noinline__ void flat_lookahead(const uint8_t* tb, const uint32_t* d
 }
 
 // ---- document starts ---------------------------------------------------------------------------------------
-__global__ void k_flat_doc_starts(WordCache C, FlatSide S) {
+// (both sides of a pair batch in one launch: blocks with an odd index take side B)
+__global__ void k_flat_doc_starts(WordCache C, FlatSide Sa, FlatSide Sb, int two) {
     pdl_wait(); pdl_trigger();
+    const bool second = two && (blockIdx.x & 1);
+    const FlatSide& S = second ? Sb : Sa;
+    const int64_t bid = two ? (blockIdx.x >> 1) : blockIdx.x, nblk = two ? ((gridDim.x + (second ? 0 : 1)) >> 1) : gridDim.x;
     const int64_t o0 = S.off[0];
     const int64_t P0 = o0 & ~(int64_t)15;
     const int64_t capq = (int64_t)S.nB * FC_BYTES - 64;
-    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d <= S.n; d += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t d = bid * blockDim.x + threadIdx.x; d <= S.n; d += nblk * blockDim.x) {
         const int64_t q = S.off[d] - P0;
         if (q < 0 || q > capq || (d > 0 && S.off[d] < S.off[d - 1])) { atomicAdd(&C.ctr[C_ERR], 1ULL); continue; }   // offsets outside the stated text
         if (d < S.n) atomicOr(&S.dsb[q >> 5], 1u << (q & 31));

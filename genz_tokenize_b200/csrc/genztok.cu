@@ -545,9 +545,10 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
             // cache guard / clear; the document-start bitmaps are zeroed by the same launch
             rc = launch_guard(h, d, st, bytes + 16, 0, F.a.dsb, (uint64_t)F.a.nB * FC_OWN + 2, b ? F.b.dsb : nullptr, b ? (uint64_t)F.b.nB * FC_OWN + 2 : 0);
             if (rc) return rc;
-            for (int s = 0; s < (b ? 2 : 1); s++) {
-                const FlatSide& S = s ? F.b : F.a;
-                { LaunchScope ls(h, d, "k_flat_doc_starts"); CU(launch_pdl(k_flat_doc_starts, dim3((unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8)), dim3(256), 0, st, d->C, S)); }
+            {
+                const unsigned per_side = (unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8);
+                LaunchScope ls(h, d, "k_flat_doc_starts");
+                CU(launch_pdl(k_flat_doc_starts, dim3(b ? 2 * per_side : per_side), dim3(256), 0, st, d->C, F.a, b ? F.b : F.a, b ? 1 : 0));
             }
             // the pad columns are written by the first k_flat_words launch on the side (tensor stores of [32 x PB] boxes)
             TmaPlanes Mp;
@@ -658,11 +659,13 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
         if (discover) {
             static const TmaPlanes no_planes{};
             FlatWordsArgs WA{};
-            for (int s = 0; s < (b ? 2 : 1); s++) {
-                const FlatSide& S = s ? F.b : F.a;
-                { LaunchScope ls(h, d, "k_flat_doc_starts"); CU(launch_pdl(k_flat_doc_starts, dim3((unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8)), dim3(256), 0, st, d->C, S)); }
-                WA.side[s] = S;
+            {
+                const unsigned per_side = (unsigned)std::min<int64_t>((n + 256) / 256, (int64_t)d->sm_count * 8);
+                LaunchScope ls(h, d, "k_flat_doc_starts");
+                CU(launch_pdl(k_flat_doc_starts, dim3(b ? 2 * per_side : per_side), dim3(256), 0, st, d->C, F.a, b ? F.b : F.a, b ? 1 : 0));
             }
+            WA.side[0] = F.a;
+            if (b) WA.side[1] = F.b;
             const uint64_t resident = (uint64_t)d->sm_count * 3;
             const uint64_t need_a = ((uint64_t)F.a.nB + FW_WARPS - 1) / FW_WARPS, need_b = b ? ((uint64_t)F.b.nB + FW_WARPS - 1) / FW_WARPS : 0;
             uint64_t blocks_a = need_a, blocks_b = need_b;
