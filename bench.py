@@ -353,7 +353,7 @@ def main():
     d0, d1 = workload.shard_range(args.pairs, rank, world)          # shard by document, no collective
     n = d1 - d0
     tok = Tokenize(devices=[local_rank])
-    tok.set_option("max_chunk_bytes", 1 << 27)                      # both sides of a 1M-pair chunk (~106 MB)
+    tok.set_option("max_chunk_bytes", max(1 << 27, 1 << int(np.ceil(np.log2(args.chunk * 112.0)))))   # both sides of a chunk (~106 MB per 1M pairs)
     for kv in os.environ.get("GENZTOK_OPTIONS", "").split(","):      # e.g. GENZTOK_OPTIONS=rows_minb=6 (experiments)
         if "=" in kv:
             tok.set_option(kv.split("=")[0], int(kv.split("=")[1]))
