@@ -21,7 +21,9 @@ Prints ONE JSON line (rank 0):
   e2e          the same metric through Tokenize.encode_batch with HOST buffers (pinned text in, pinned planes out), copies timed
   cpu_baseline the UNMODIFIED Python reference (oracle/_ref) on this host: one process and multiprocessing.Pool(all cores); the C
                restatement (oracle/) beside it
-  extra        BASELINE configs[1] (1M singles, max_len 128), configs[3] (decode of the planes), configs[4] (custom vocab, long documents)
+  extra        BASELINE configs[1] (1M singles, max_len 128: device-resident, cold, and end to end through the host API), configs[3] (decode of
+               the planes into a reused text ring), the reference's default call shape (ragged rows, host API), configs[4] (custom vocab,
+               long documents, cold and warm)
 `--impl reference` times the reference itself (Pool over all cores) on a bounded sample of the same workload.
 """
 import argparse
