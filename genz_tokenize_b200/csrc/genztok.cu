@@ -66,6 +66,7 @@ struct DeviceCtx {
     DevTables T{};
     WordCache C{};
     bool cache_ready = false;
+    uint64_t cache_bytes = 0;                     // the chunk size the word cache is sized for
     bool cache_empty = true;                      // no word has been looked up since the cache was created or reset: the next text is all new
     bool force_wide = false;
     std::vector<void*> table_allocs;
@@ -121,6 +122,7 @@ struct genztok {
     std::mutex err_mu;                   // guards err / prof_names (device worker threads)
     // options
     int64_t max_chunk_bytes = 64ll << 20;
+    int64_t fixed_cache = 0;             // size the word cache for max_chunk_bytes at once instead of by the chunks met (test knob)
     int64_t chunk_rows = 1ll << 18;     // rows per chunk of the host path: small enough that the copies of neighbouring chunks overlap the kernels
     int64_t force_group = 0;
     int64_t force_wide = 0;              // stage rows as int32 even when ids fit uint16 (test knob)
@@ -283,10 +285,17 @@ int stream_leave(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
 
 uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
-int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
-    if (d->cache_ready) return GENZTOK_OK;
-    const uint64_t B = (uint64_t)h->max_chunk_bytes;
+// The word cache is sized for the worst case of ONE chunk (every second byte a new word), so its size follows the largest chunk this
+// device has met (a power of two from 1 MiB up, at most max_chunk_bytes): a handle that only sees small batches keeps a 32 MiB table
+// instead of the 2 GiB that max_chunk_bytes = 64 MiB would cost.  A larger chunk regrows it (and empties it).
+int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st, int64_t chunk_bytes) {
+    const uint64_t limit = (uint64_t)h->max_chunk_bytes;
+    const uint64_t need = std::min<uint64_t>(limit, (uint64_t)std::max<int64_t>(chunk_bytes, 0) + 64);
+    if (d->cache_ready && need <= d->cache_bytes) return GENZTOK_OK;
+    const uint64_t B = h->fixed_cache ? limit : std::min<uint64_t>(limit, std::max<uint64_t>(next_pow2(need), 1ull << 20));
     const uint64_t slots = std::max<uint64_t>(next_pow2(B), 1024);
+    const bool regrow = d->cache_ready;
+    if (regrow) CU(cudaDeviceSynchronize());                       // nothing may still be using the arrays that are about to be freed
     CU(d->slots.ensure(slots * sizeof(Slot)));
     CU(d->key_arena.ensure(B + B / 3 + 128));                      // (long keys are stored 8-byte aligned: up to 7 bytes of padding for 25 or more)
     CU(d->tok_arena.ensure((2 * B + 64) * 4));
@@ -295,7 +304,11 @@ int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     CU(d->rank_scratch.ensure((B + 64) * 4));
     // on the stream that runs the kernels of this call (the handle's own stream is non-blocking: nothing else orders it with the caller's)
     CU(cudaMemsetAsync(d->slots.p, 0, slots * sizeof(Slot), st));
-    CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, st));
+    if (!regrow) CU(cudaMemsetAsync(d->ctr.p, 0, C_COUNT * 8, st));
+    else {                                                           // keep the cumulative counters (errors, tokens)
+        CU(cudaMemsetAsync(d->ctr.p, 0, (size_t)C_ERR * 8, st));
+        CU(cudaMemsetAsync(d->ctr.as<unsigned long long>() + C_TOKENS + 1, 0, (size_t)(C_COUNT - C_TOKENS - 1) * 8, st));
+    }
     WordCache& C = d->C;
     C.slots = d->slots.as<Slot>(); C.mask = (uint32_t)(slots - 1);
     C.key_arena = d->key_arena.as<uint8_t>(); C.key_cap = B + B / 3 + 64;
@@ -305,6 +318,7 @@ int ensure_cache(genztok_t* h, DeviceCtx* d, cudaStream_t st) {
     C.rank_scratch = d->rank_scratch.as<uint32_t>(); C.rank_cap = B + 64;
     d->cache_ready = true;
     d->cache_empty = true;
+    d->cache_bytes = B;
     return GENZTOK_OK;
 }
 
@@ -496,10 +510,10 @@ int encode_fixed_on_device(genztok_t* h, DeviceCtx* d, cudaStream_t st, const Si
     LaunchScope::cur_stream = st;
     int rc = stream_enter(h, d, st);
     if (rc) return rc;
-    rc = ensure_cache(h, d, st);
-    if (rc) return rc;
     const int64_t bytes = a.nbytes + (b ? b->nbytes : 0);
     if (bytes > h->max_chunk_bytes) return fail(h, GENZTOK_E_LIMIT, "chunk of %lld bytes exceeds max_chunk_bytes=%lld", (long long)bytes, (long long)h->max_chunk_bytes);
+    rc = ensure_cache(h, d, st, bytes + 32);
+    if (rc) return rc;
     if (n <= 0) return GENZTOK_OK;
     CU(d->redo.ensure((size_t)n * 4));
     CU(d->fix.ensure((size_t)n * 4));
@@ -887,7 +901,9 @@ void genztok_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int genztok_set_option(genztok_t* h, const char* name, int64_t value) {
     std::string n = name ? name : "";
-    if (n == "max_chunk_bytes") {
+    if (n == "fixed_cache") {
+        h->fixed_cache = value;
+    } else if (n == "max_chunk_bytes") {
         for (DeviceCtx* d : h->devs) if (d->cache_ready) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes must be set before the first encode");
         if (value < 4096 || value > (1ll << 29)) return fail(h, GENZTOK_E_INVALID, "max_chunk_bytes must be in [4 KiB, 512 MiB]");
         h->max_chunk_bytes = value;
@@ -1089,7 +1105,14 @@ void encode_rows_on_device(genztok_t* h, DeviceCtx* d, const EncodeJob& J, int64
             r0 = r1;
         }
     }
-    FAIL_RC(ensure_cache(h, d, st));
+    {
+        int64_t most = 0;                                            // the largest chunk of this call
+        for (size_t ci = 0; ci + 1 < cuts.size(); ci++) {
+            const int64_t a0 = cuts[ci], a1 = cuts[ci + 1];
+            most = std::max<int64_t>(most, (J.text_off[a1] - J.text_off[a0]) + (has_pair ? J.pair_off[a1] - J.pair_off[a0] : 0) + 64);
+        }
+        FAIL_RC(ensure_cache(h, d, st, most));
+    }
     unsigned long long tokens_before = 0;
     CUF(cudaMemcpyAsync(&tokens_before, d->C.ctr + C_TOKENS, 8, cudaMemcpyDeviceToHost, st));
     CUF(cudaStreamSynchronize(st));

@@ -302,6 +302,33 @@ def test_flat_pipeline_text_edges(oracle):
     assert_matches_oracle(be, orc, what="flat edges chunked")
 
 
+def test_word_cache_follows_the_chunk_size(oracle):
+    # the word cache is sized for the worst case of one chunk: a handle that only sees small batches must not take the 3 GiB that
+    # max_chunk_bytes = 64 MiB costs; a larger batch regrows (and empties) it, a smaller one afterwards reuses it; results unchanged
+    import torch
+    from genz_tokenize_b200 import Tokenize, workload
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    t = Tokenize(devices=[0])
+    small = workload.generate(41, 2000, 0, 13, 0.02)
+    ref_small = oracle.encode_batch(small, None, threads=8, max_len=32)
+    assert_matches_oracle(t.encode_batch(small, max_len=32), ref_small, what="small batch, small cache")
+    torch.cuda.synchronize()
+    used_small = free0 - torch.cuda.mem_get_info(0)[0]
+    assert used_small < (400 << 20), used_small
+    big = workload.generate(42, 300000, 3, 13, 0.01)                      # ~15 MB: the cache regrows
+    assert_matches_oracle(t.encode_batch(big, max_len=32), oracle.encode_batch(big, None, threads=8, max_len=32), what="large batch, regrown cache")
+    torch.cuda.synchronize()
+    used_big = free0 - torch.cuda.mem_get_info(0)[0]
+    assert used_big > used_small
+    assert_matches_oracle(t.encode_batch(small, max_len=32), ref_small, what="small batch again")
+    assert_matches_oracle(t.encode_batch(small), oracle.encode_batch(small, None, threads=8), what="small batch, ragged")
+    assert t.check_errors() == 0
+    fixed = Tokenize(devices=[0])
+    fixed.set_option("fixed_cache", 1)                                    # the old behaviour, on request
+    assert_matches_oracle(fixed.encode_batch(small, max_len=32), ref_small, what="small batch, full-size cache")
+
+
 def test_decode_roundtrip_batch(tok, oracle):
     from genz_tokenize_b200 import workload
     t = workload.generate(301, 4000, 3, 13, 0.02)
