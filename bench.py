@@ -480,6 +480,11 @@ def main():
             lib.genztok_host_free(hp)
         del pins
 
+    # ---- what the box gives all ranks at once over PCIe (the ceiling of the end-to-end leg; tools/pcie_probe.py is the long form) ----
+    box = None
+    if args.e2e_steps > 0 and ne > 0:
+        box = pcie_box_probe(torch, dist, world, dev)
+
     # ---- side measurements (N = 1 only; reported under "extra", not the headline) ------------------------------------------
     extra = None
     if world == 1 and not args.no_extras:
@@ -549,7 +554,8 @@ def main():
                                     "note": "all kernels and launch gaps of a step against n_gpus x peak: the number to compare with the 50% target"}},
         "e2e": {"value": tot_e2e_tokens / (e2e_step_ms * 1e-3) if e2e_ms else None, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_step_ms, "pairs_per_step_per_gpu": ne, "d2h_gb_per_s_per_rank": d2h / (e2e_step_ms * 1e-3) / 1e9 if e2e_ms else None,
-                "api": "Tokenize.encode_batch(packed pairs in pinned host memory) -> pinned numpy planes; a bounded share (%d pairs per GPU) of the batch per step" % ne},
+                "api": "Tokenize.encode_batch(packed pairs in pinned host memory) -> pinned numpy planes; a bounded share (%d pairs per GPU) of the batch per step" % ne,
+                "box_pcie": box},
         "gpu_launches": int(tot_launches),
         "clocks": clocks,
         "kernels": kernels,
@@ -566,6 +572,39 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def pcie_box_probe(torch, dist, world, dev, mb=256, reps=4):
+    """Plain pinned-memory copies by every rank at once: device->host alone, and both directions together (GB/s per direction)."""
+    h_out = torch.empty(mb << 20, dtype=torch.uint8).pin_memory()
+    h_in = torch.zeros(mb << 20, dtype=torch.uint8).pin_memory()
+    d_a = torch.zeros(mb << 20, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def leg(both):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                h_out.copy_(d_a, non_blocking=True)
+            if both:
+                with torch.cuda.stream(s2):
+                    d_b.copy_(h_in, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * (mb << 20) / (time.perf_counter() - t0) / 1e9
+
+    leg(True)
+    v = torch.tensor([leg(False), leg(True)], dtype=torch.float64, device=dev)
+    lo = v.clone()
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return {"d2h_gb_per_s_all_ranks": float(v[0]), "d2h_gb_per_s_slowest_rank": float(lo[0]),
+            "both_directions_gb_per_s_per_direction_all_ranks": float(v[1]), "both_directions_slowest_rank": float(lo[1]),
+            "what": "cudaMemcpyAsync of %d MiB pinned buffers by all %d ranks at once: the ceiling the host side of this box puts on the end-to-end leg" % (mb, world)}
 
 
 def run_extras(torch, tok, S, dev, peak, workload, Tokenize):
