@@ -61,3 +61,18 @@ def test_data_collection_like_the_reference():
     assert back.data_ptr() == ids.data_ptr()
     both = DataCollection.from_encoding(enc, y, dec=enc)
     assert list(both.fields()) == ["input_ids", "attention_mask", "dec_input_ids", "dec_attention_mask", "y"]
+
+
+def test_device_reader_needs_a_gpu(tmp_path):
+    # iter_device_batches has no host fallback: without CUDA it fails at once (and leaves no reader thread behind)
+    import threading
+    import torch
+    from genz_tokenize_b200 import iter_device_batches
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by test_file_to_device_batches_handoff")
+    p = tmp_path / "docs.txt"
+    p.write_bytes(b"mot hai ba\nbon nam\n")
+    before = threading.active_count()
+    with pytest.raises(Exception):
+        next(iter_device_batches(str(p), docs_per_batch=1))
+    assert threading.active_count() == before
