@@ -196,13 +196,18 @@ int64_t genztok_launch_count(const genztok_t *h);         /* kernels launched by
  * {"kernel": {"launches": L, "ms": T}, ...}; returns the length needed. */
 int genztok_set_profiling(genztok_t *h, int on);
 int64_t genztok_profile_report(genztok_t *h, char *buf, int64_t cap, int reset);
-/* Engine knobs.  Sizing: "max_chunk_bytes" (before the first encode; sizes the word cache for its worst case),
- * "chunk_rows".  Pipeline selection and test knobs, all defaulting to the fastest correct setting: "no_flat" (1: fused row kernel
+/* Engine knobs.  Sizing: "max_chunk_bytes" (before the first encode; the largest chunk a call may hand over: the
+ * word cache is sized for the worst case of the largest chunk met so far, up to this), "fixed_cache" (1: size it for
+ * max_chunk_bytes at once), "chunk_rows".  Pipeline selection and test knobs, all defaulting to the fastest correct setting: "no_flat" (1: fused row kernel
  * even where the byte-parallel pipeline applies), "no_tma" (store instructions instead of the TMA unit), "no_fixed_decode" (fixed-width rows through the any-rows decode kernels),
  * "no_token_decode" (ragged rows decoded by a warp per row instead of a thread per id), "tma_columns" (staged
  * columns per row, multiple of 16, 0 = from the text size), "no_side_pads", "flat_rows" (rows per tile of k_flat_rows, 1..32),
  * "rows_minb" / "words_minb" / "rows_grid" (occupancy of the pipeline's kernels), "group" (documents per tile of the fused
- * kernel, 0 = auto), "wide_rows", "grid_mult".  Unknown names are an error. */
+ * kernel, 0 = auto), "wide_rows", "grid_mult", "no_stage32" (1: never narrow the staged columns to 32 by the previous call's row
+ * lengths), "no_discovery" (1: no byte-parallel word pass in front of the fused row kernel on an empty cache), "decode_write"
+ * (fixed-width decode, write pass: 0 = by the rows' average lead, 1 = warp per row, 2 / 3 = lane per junction with 256 / 512 bytes),
+ * "decode_wide_max" (average lead up to which the 512-byte junctions are taken), "copy_round", "copy_blocks", "no_copy_kernel"
+ * (host path: how the result columns travel back).  Unknown names are an error. */
 int genztok_set_option(genztok_t *h, const char *name, int64_t value);
 
 /* Error counter of the asynchronous device path (genztok_encode_device / genztok_decode_device do not synchronise, so they
