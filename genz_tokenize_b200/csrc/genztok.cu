@@ -138,7 +138,7 @@ struct genztok {
     int64_t no_copy_kernel = 0;          // host path: trimmed planes go back through cudaMemcpy2DAsync instead of k_copy_out (test knob)
     int64_t copy_blocks = 64;            // blocks of k_copy_out
     int64_t copy_round = 64;             // columns the one-byte planes' copy-out is rounded up to (32 or 64: whole 64-byte lines of host memory)
-    int64_t l2_policy = 0;               // bit 0: text read evict-first, bit 1: word arrays stored evict-last (k_flat_words; experiments)
+    int64_t l2_policy = 2;               // k_flat_words: bit 0: text read evict-first (slower), bit 1: word arrays stored evict-last (default: -3.5 % per chunk)
     int64_t rows_pad_pct = 0;            // share of the pad columns (percent of the 32-row tiles, the last ones) that k_flat_rows stores instead of k_flat_words
     int64_t rows_grid = 0;               // cap on resident blocks per SM of k_flat_rows (0 = as many as fit)
     int64_t rows_minb = 0, words_minb = 3;   // resident 256-thread blocks per SM the flat kernels are compiled for (rows: 0 = 3 for pairs, 5 for single sentences)
